@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- Mpoints/s fused + map-update frames/s of the fusion path (BASELINE.json metric).
+
+A "step" is one frame = one ElevationMap.input_pointcloud() call = everything in the reference's
+update_map_with_kernel (elevation_mapping.py:316-391): error count -> drift -> Kalman fusion ->
+ray-cast cleanup -> average -> overlap clear -> dilation -> traversability -> normals.
+
+Workload at N=1 = BASELINE.json configs[1]: 1024x1024 grid, 0.04 m, 200k-point LiDAR-like cloud per
+frame, ray-cast + overlap clear on (SURVEY.md 8(d) "B").  At N>1 (torchrun, one rank per GPU) the
+workload is configs[2] generalised: one 200k-point sensor per GPU fused into a replicated grid with
+an NCCL all-reduce of the per-cell partials (weak scaling: per-GPU work fixed).
+
+Between timed frames, untimed: move_to (recentre on the sensor), update_variance, update_time (the
+reference runs these from timers) and an L2 flush (a 512 MB memset) -- say so in `config`.
+`value`: inputs resident in HBM, each frame timed with CUDA events on the launching stream.
+`e2e`:   the same frames through the public API with pinned HOST buffers: H2D copy of the cloud and a
+         D2H read of the frame statistics inside the timed region.
+`--impl reference` times the reference's own kernel source (oracle/_ref, compiled for the host by
+oracle/build_ref.py with OpenMP + atomics) on all host threads, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mpoints/s fused (1024^2 grid, 200k-pt LiDAR frames, raycast+overlap-clear on)"
+N_FRAME_POOL = 8          # distinct synthetic frames, cycled
+PTS_PER_SENSOR = 200000
+
+
+def make_frames(n_sensors, sensor, n_pool):
+    from elevation_mapping_cupy_b200 import workloads as wl
+    out = []
+    for f in range(n_pool):
+        pts, R, t = wl.lidar_cloud(1 if n_sensors == 1 else 2, f, sensor=sensor, n_sensors=n_sensors)
+        out.append((pts, R, t))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_port(param, frames, max_seconds=20.0):
+    """The oracle (C restatement, all host threads) on a bounded sample of the same workload."""
+    from oracle import oracle as O
+    om = O.OracleElevationMap(param, nthreads=0)
+    cores = O.lib().oracle_max_threads()
+    npts, t_total, n = 0, 0.0, 0
+    t_begin = time.perf_counter()
+    for pts, R, t in frames:
+        om.move_to(t, R)
+        t0 = time.perf_counter()
+        om.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+        t_total += time.perf_counter() - t0
+        om.update_variance(); om.update_time()
+        npts += len(pts); n += 1
+        if time.perf_counter() - t_begin > max_seconds:
+            break
+    return {"value": npts / t_total / 1e6, "unit": "Mpoints/s", "cores": int(cores), "kind": "port",
+            "sample": f"{n} frames of the same 200k-pt workload, oracle/emap_oracle.c with OpenMP", "frames_per_s": n / t_total}
+
+
+def run_reference_arm(args):
+    """Reference arm: the reference's own kernel source (oracle/_ref) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from oracle import oracle as O
+    param = core_parameter(1024)
+    try:
+        rm = O.RefKernelMap(param, "core1024", parallel=True)
+    except Exception as e:       # prebuilt library absent
+        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref not built: {e}"[:200]}))
+        return 0
+    cores = O.lib().oracle_max_threads()
+    n_sensors = max(1, args.gpus)
+    pools = [make_frames(n_sensors, s, min(N_FRAME_POOL, args.warmup + args.steps)) for s in range(n_sensors)]
+    times = []
+    for it in range(args.warmup + args.steps):
+        f = it % len(pools[0])
+        rm.move_to(pools[0][f][2], pools[0][f][1])
+        t0 = time.perf_counter()
+        for s in range(n_sensors):                       # the reference fuses sensors sequentially
+            pts, R, t = pools[s][f]
+            rm.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+        dt = time.perf_counter() - t0
+        rm.update_variance(); rm.update_time()
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    val = n_sensors * PTS_PER_SENSOR / (ms * 1e-3) / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpoints/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "1024x1024 grid, 0.04 m, %d x 200k-pt LiDAR frame(s), raycast+overlap-clear on" % n_sensors,
+                       "frames_per_s": 1e3 / ms},
+            "cpu_baseline": {"value": val, "unit": "Mpoints/s", "cores": int(cores), "kind": "reference",
+                             "sample": f"{args.steps} frames; reference kernel source (custom_kernels.py) compiled for the "
+                                       "host by oracle/build_ref.py, OpenMP + CAS atomics; traversability via torch CPU conv"},
+            "e2e": {"value": val, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="keep the map L2-resident between frames (reported separately)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200.elevation_mapping import ElevationMap
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+
+    param = core_parameter(1024)
+    em = ElevationMap(param, device=local_rank)
+    frames = make_frames(world, rank, N_FRAME_POOL)
+    frames0 = frames if rank == 0 or world == 1 else None
+    sh = None
+    if world > 1:
+        from elevation_mapping_cupy_b200.sharded import ShardedElevationMap
+        sh = ShardedElevationMap(em, static_offsets=(rank * PTS_PER_SENSOR, world * PTS_PER_SENSOR))
+        # every replica recentres on sensor 0's pose
+        from elevation_mapping_cupy_b200 import workloads as wl
+        poses0 = [wl.lidar_pose(f, 0, world) for f in range(N_FRAME_POOL)]
+    else:
+        poses0 = [(R, t) for (_, R, t) in frames]
+
+    dev_pts = [torch.from_numpy(p).cuda() for p, _, _ in frames]
+    pin_pts = [torch.from_numpy(p).pin_memory() for p, _, _ in frames]
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+    if sh is None:
+        em._check(em._L.emap_set_stream(em._h, torch.cuda.current_stream().cuda_stream))
+
+    def between(f):
+        R0, t0 = poses0[f]
+        em.move_to(t0, R0)
+        em.update_variance(); em.update_time()
+        if not args.no_flush:
+            flush.zero_()
+
+    def frame(f, pts):
+        _, R, t = frames[f]
+        if sh is None:
+            em.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+        else:
+            sh.input_sensors([pts], [R], [t], 0.02, 0.02, device_ptrs=pts.is_cuda, overlap_z=float(poses0[f][1][2]))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(n_warm, n_steps, host):
+        src = pin_pts if host else dev_pts
+        for it in range(n_warm):
+            f = it % N_FRAME_POOL
+            between(f); frame(f, src[f])
+            if host:
+                em.get_frame_stats()
+        barrier()
+        evs, wall = [], 0.0
+        launches0 = em.launch_count()
+        for it in range(n_steps):
+            f = (n_warm + it) % N_FRAME_POOL
+            between(f)
+            if host:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                frame(f, src[f])
+                em.get_frame_stats()                     # D2H read of the step's result (syncs)
+                wall += time.perf_counter() - t0
+            else:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream); frame(f, src[f]); e1.record(stream)
+                evs.append((e0, e1))
+        launches = em.launch_count() - launches0
+        barrier()
+        if host:
+            ms = 1e3 * wall / n_steps
+        else:
+            ms = sum(a.elapsed_time(b) for a, b in evs) / n_steps
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches
+
+    # ---- device-resident arm (value) with clocks sampled during the timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = run(args.warmup, args.steps, host=False)
+    clocks = sampler.stop() if rank == 0 else None
+    # launches inside the timed frames only (exclude move_to / ticks): count one frame precisely
+    between(0); torch.cuda.synchronize(); l0 = em.launch_count(); frame(0, dev_pts[0]); torch.cuda.synchronize()
+    launches_per_frame = em.launch_count() - l0
+
+    # ---- per-stage device times (CUDA events inside the library, same stream) for the roofline
+    em.enable_stage_timing(True)
+    stage = np.zeros(8)
+    n_st = min(20, max(5, args.steps // 5))
+    for it in range(n_st):
+        f = it % N_FRAME_POOL
+        between(f); frame(f, dev_pts[f]); torch.cuda.synchronize()
+        stage += em.stage_ms()
+    stage /= n_st
+    em.enable_stage_timing(False)
+    em._check(em._L.emap_set_ray_counting(em._h, 1))
+    between(0); frame(0, dev_pts[0]); st = em.get_frame_stats()
+    em._check(em._L.emap_set_ray_counting(em._h, 0))
+
+    # ---- end-to-end arm: pinned host buffers through the public API, stats read back every step
+    ms_e2e, _ = run(max(3, args.warmup // 2), args.steps, host=True)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    n_total = world * PTS_PER_SENSOR
+    value = n_total / (ms * 1e-3) / 1e6
+    e2e = n_total / (ms_e2e * 1e-3) / 1e6
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    C = param.cell_n ** 2
+    names = ["index+error", "drift", "fusion", "record", "raycast", "finalize", "post(dilate+cnn+normal)"]
+    dom = int(np.argmax(stage[:7]))
+    # algorithmic bytes per launch of each stage (DESIGN.md "bytes per unit")
+    N = PTS_PER_SENSOR
+    alg = {"index+error": 12 * N + 20 * N + 16 * N, "drift": 64, "fusion": 20 * N + 12 * N + 28 * N,
+           "record": 36 * C + 16 * C, "raycast": 20 * N + 16 * C, "finalize": 24 * C + 28 * C + 24 * C,
+           "post(dilate+cnn+normal)": 12 * C + 20 * C}
+    dom_name = names[dom]
+    ach = alg[dom_name] / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
+    frame_bytes = 24 * N * world + 80 * C
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": hbm, "unit": "GB/s",
+                "frac": ach / hbm, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": float(stage[dom]), "kernel_share_of_frame": float(stage[dom] / max(stage[7], 1e-9)),
+                "frame_algorithmic_bytes": frame_bytes,
+                "frame_achieved_gbs": frame_bytes / (ms * 1e-3) / 1e9, "frame_frac": frame_bytes / (ms * 1e-3) / 1e9 / hbm,
+                "stage_ms": {n: float(v) for n, v in zip(names + ["total"], stage)}}
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_baseline_port(param, frames0[:4])
+    line = {"metric": METRIC, "value": value, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "1024x1024 grid, 0.04 m, %d x 200k-pt LiDAR-like frame(s) per step, raycast+overlap-clear on, "
+                                   "drift compensation on (BASELINE configs[%d])" % (world, 1 if world == 1 else 2),
+                       "frames_per_s": 1e3 / ms, "points_per_step": n_total,
+                       "parallelism": "1 GPU" if world == 1 else f"{world} sensor shards, replicated grid, NCCL int all-reduce x3",
+                       "l2": "flushed between timed frames (512 MB memset, untimed)" if not args.no_flush else "warm (no flush)",
+                       "untimed_between_frames": "move_to, update_variance, update_time",
+                       "ray_steps_per_frame": int(st.ray_steps), "ray_cell_visits_per_frame": int(st.ray_visits),
+                       "valid_points_per_frame": int(st.n_valid_points)},
+            "e2e": {"value": e2e, "unit": "Mpoints/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(PTS_PER_SENSOR * 12),
+                    "d2h_bytes_per_step": 72, "note": "pinned host cloud -> emap_input_pointcloud (H2D inside), frame stats read back"},
+            "gpu_launches": int(launches_per_frame * args.steps), "gpu_launches_per_frame": int(launches_per_frame),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,786 @@
+// emap_api.cu -- C ABI of libemap.so (see include/emap.h) and host-side orchestration.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see elevation_mapping_cupy_b200/build.py)
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/emap.h"
+#include "emap_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct StageTimer {
+  cudaEvent_t ev[9];
+  bool have = false;
+};
+
+}  // namespace
+
+struct emap_handle {
+  emap_config cfg;
+  DevCfg dc;
+  int device = 0;
+  std::mutex mu;
+  std::string err;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, own_stream = nullptr;
+  // state
+  float* map = nullptr;       // (7,W,W)
+  float* map_alt = nullptr;   // shift target
+  float* normal = nullptr;    // (3,W,W)
+  float* trav_input = nullptr;
+  float center[3] = {0, 0, 0};        // fp32 like EM.py:61
+  float base_rotation[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  // scratch
+  CellScratch sc{};
+  u32* u32_block = nullptr;   // cnt_all | cnt_inl | cnt_fused | n_out | n_ray
+  i64* i64_block = nullptr;   // SH | SV | DV
+  int* ukey_x = nullptr;      // exchange copy of the upper-bound keys (sharded frames)
+  FrameScalars* fs = nullptr;
+  float* steps = nullptr;     // device copy of the march table
+  std::vector<float> steps_host;
+  // points
+  void* d_in[2] = {nullptr, nullptr};
+  size_t d_in_bytes[2] = {0, 0};
+  cudaEvent_t in_free[2] = {nullptr, nullptr}, copy_done = nullptr;
+  int in_sel = 0;
+  float4* xyzv = nullptr;
+  int* pidx = nullptr;
+  i64 pt_cap = 0;
+  // last frame description
+  std::vector<Pose> poses;
+  std::vector<i64> offs;      // n_sensors + 1
+  i64 n_points = 0, global_off = 0;
+  float pos_noise = 0, ori_noise = 0;
+  int phase = 0;              // sharded-frame state machine
+  // export staging
+  float* d_export = nullptr;
+  // plugin scratch
+  float* pl[4] = {nullptr, nullptr, nullptr, nullptr};
+  int* pl_cnt = nullptr;
+  int pl_cnt_cap = 0;
+  // misc
+  int64_t launches = 0;
+  int count_rays = 0;
+  int timing = 0;
+  StageTimer st;
+  float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
+      return EMAP_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+#define LAUNCH_CHECK()                                                                    \
+  do {                                                                                    \
+    h->launches++;                                                                        \
+    cudaError_t e_ = cudaGetLastError();                                                  \
+    if (e_ != cudaSuccess) {                                                              \
+      h->err = std::string("kernel launch: ") + cudaGetErrorString(e_);                   \
+      return EMAP_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+inline float h16_host(float x) { return __half2float(__float2half_rn(x)); }
+
+inline int cdiv(i64 a, int b) { return (int)((a + b - 1) / b); }
+
+int fail(emap_handle* h, int code, const char* msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+void make_pose(const float* R, const float* t_rel, Pose* q) {
+  for (int i = 0; i < 9; i++) q->R16[i] = h16_host(R[i]);
+  for (int i = 0; i < 3; i++) { q->t16[i] = h16_host(t_rel[i]); q->t[i] = t_rel[i]; }
+}
+
+void fill_devcfg(const emap_config& c, DevCfg& d) {
+  memset(&d, 0, sizeof(d));
+  d.W = c.cell_n; d.C = c.cell_n * c.cell_n;
+  d.dilation = c.dilation_size; d.edge_sharpen = c.enable_edge_sharpen; d.drift_en = c.enable_drift_compensation;
+  d.visibility = c.enable_visibility_cleanup; d.overlap = c.enable_overlap_clearance;
+  // EM.py:87-91
+  int cell_range = (int)(c.overlap_clear_range_xy / c.resolution);
+  if (cell_range < 0) cell_range = 0;
+  if (cell_range > c.cell_n) cell_range = c.cell_n;
+  d.cell_min = c.cell_n / 2 - cell_range / 2; d.cell_max = c.cell_n / 2 + cell_range / 2;
+  d.resolution = c.resolution; d.half_w = 0.5 * (double)c.cell_n;
+  d.snf = c.sensor_noise_factor; d.mahal = c.mahalanobis_thresh; d.outlier_var = c.outlier_variance;
+  d.inlier_var_half = c.drift_compensation_variance_inlier / 2.0; d.trav_inlier = c.traversability_inlier;
+  d.wall_thresh = c.wall_num_thresh; d.min_drift_cnt = c.min_height_drift_cnt;
+  d.max_ray_length = c.max_ray_length; d.cleanup_step = c.cleanup_step; d.cos_thresh = c.cleanup_cos_thresh;
+  d.mvd2 = c.min_valid_distance * c.min_valid_distance; d.max_height = c.max_height_range;
+  d.ramp_a = c.ramped_height_range_a; d.ramp_b = c.ramped_height_range_b; d.ramp_c = c.ramped_height_range_c;
+  d.max_variance = c.max_variance; d.pos_thresh = c.position_noise_thresh; d.ori_thresh = c.orientation_noise_thresh;
+  d.inv_res_f = (float)(1.0 / c.resolution); d.half_w_f = (float)(0.5 * (double)c.cell_n);
+  d.c_out = (float)c.outlier_variance; d.init_var = (float)c.initial_variance;
+  d.max_drift_f = (float)c.max_drift; d.drift_alpha_f = (float)c.drift_compensation_alpha;
+  d.max_len16 = h16_host((float)c.max_ray_length);
+  d.res_f = (float)c.resolution;
+  d.overlap_z_f = (float)c.overlap_clear_range_z; d.time_var_f = (float)c.time_variance;
+  d.time_int_f = (float)c.time_interval;
+}
+
+// CK.py:203,268: the fp16 march variable, identical for every ray
+void build_steps(const emap_config& c, float max_len16, std::vector<float>& out) {
+  const double ray_step = c.resolution / std::sqrt(2.0);
+  out.clear();
+  float s = h16_host((float)ray_step);
+  while (s < max_len16 && out.size() < 65536) {
+    out.push_back(s);
+    float nx = h16_host((float)((double)s + ray_step));
+    if (!(nx > s)) break;      // fp16 spacing exceeded the step: the reference would spin forever
+    s = nx;
+  }
+}
+
+int ensure_points(emap_handle* h, i64 n) {
+  if (n <= h->pt_cap) return 0;
+  i64 cap = n + n / 4 + 1024;
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->xyzv) cudaFree(h->xyzv);
+  if (h->pidx) cudaFree(h->pidx);
+  h->xyzv = nullptr; h->pidx = nullptr; h->pt_cap = 0;
+  CK(cudaMalloc(&h->xyzv, sizeof(float4) * cap));
+  CK(cudaMalloc(&h->pidx, sizeof(int) * cap));
+  h->pt_cap = cap;
+  return 0;
+}
+
+int ensure_in(emap_handle* h, int b, size_t bytes) {
+  if (bytes <= h->d_in_bytes[b]) return 0;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaStreamSynchronize(h->copy_stream));
+  if (h->d_in[b]) cudaFree(h->d_in[b]);
+  h->d_in[b] = nullptr; h->d_in_bytes[b] = 0;
+  size_t cap = bytes + bytes / 4 + 4096;
+  CK(cudaMalloc(&h->d_in[b], cap));
+  h->d_in_bytes[b] = cap;
+  return 0;
+}
+
+int stage_mark(emap_handle* h, int k) {
+  if (!h->timing) return 0;
+  CK(cudaEventRecord(h->st.ev[k], h->stream));
+  return 0;
+}
+
+template <typename T>
+int launch_index(emap_handle* h, const Pose& q, const T* pts, i64 n, i64 stride, i64 off) {
+  if (n <= 0) return 0;
+  k_index_error<T><<<cdiv(n, 256), 256, 0, h->stream>>>(h->dc, q, pts, n, stride, h->xyzv + off, h->pidx + off, h->map,
+                                                           h->sc.cnt_all, h->sc.cnt_inl, h->fs);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// phase 0: upload + index/error pass for every sensor
+int frame_begin(emap_handle* h, int32_t n_sensors, const void* const* points, const int64_t* n, int64_t row_stride,
+                int dtype, int is_device_ptr, const float* R, const float* t, int64_t global_off, float pn, float on) {
+  if (n_sensors < 1 || row_stride < 3 || (dtype != EMAP_F32 && dtype != EMAP_F64))
+    return fail(h, EMAP_ERR_INVALID, "emap_input: n_sensors >= 1, row_stride >= 3, dtype f32/f64 required");
+  const size_t esz = dtype == EMAP_F32 ? 4 : 8;
+  h->offs.assign(n_sensors + 1, 0);
+  for (int s = 0; s < n_sensors; s++) {
+    if (n[s] < 0 || (n[s] > 0 && !points[s])) return fail(h, EMAP_ERR_INVALID, "emap_input: bad point array");
+    h->offs[s + 1] = h->offs[s] + n[s];
+  }
+  const i64 N = h->offs[n_sensors];
+  if (global_off + N >= (1ll << 31)) return fail(h, EMAP_ERR_INVALID, "emap_input: more than 2^31 points in a frame");
+  h->n_points = N; h->global_off = global_off; h->pos_noise = pn; h->ori_noise = on;
+  int rc = ensure_points(h, N);
+  if (rc) return rc;
+  h->poses.resize(n_sensors);
+  for (int s = 0; s < n_sensors; s++) {
+    float tr[3];
+    for (int k = 0; k < 3; k++) tr[k] = t[3 * s + k] - h->center[k];      // EM.py:314,333 (fp32)
+    make_pose(R + 9 * s, tr, &h->poses[s]);
+  }
+  // frame scalars: keep mean / additive error, zero the accumulators
+  CK(cudaMemsetAsync(h->fs, 0, offsetof(FrameScalars, shift), h->stream));
+  {
+    float tz = h->poses[0].t[2];
+    CK(cudaMemcpyAsync(&h->fs->overlap_tz, &tz, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  }
+  if (stage_mark(h, 0)) return EMAP_ERR_CUDA;
+  const void* dev_pts[64];
+  std::vector<const void*> dev_vec;
+  const void** dp = dev_pts;
+  if (n_sensors > 64) { dev_vec.resize(n_sensors); dp = dev_vec.data(); }
+  if (is_device_ptr) {
+    for (int s = 0; s < n_sensors; s++) dp[s] = points[s];
+  } else {
+    const int b = h->in_sel; h->in_sel ^= 1;
+    size_t total = 0;
+    for (int s = 0; s < n_sensors; s++) total += (size_t)n[s] * row_stride * esz;
+    rc = ensure_in(h, b, total);
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(h->copy_stream, h->in_free[b], 0));
+    size_t o = 0;
+    for (int s = 0; s < n_sensors; s++) {
+      const size_t bytes = (size_t)n[s] * row_stride * esz;
+      if (bytes) CK(cudaMemcpyAsync((char*)h->d_in[b] + o, points[s], bytes, cudaMemcpyHostToDevice, h->copy_stream));
+      dp[s] = (char*)h->d_in[b] + o;
+      o += bytes;
+    }
+    CK(cudaEventRecord(h->copy_done, h->copy_stream));
+    CK(cudaStreamWaitEvent(h->stream, h->copy_done, 0));
+  }
+  for (int s = 0; s < n_sensors; s++) {
+    rc = dtype == EMAP_F32 ? launch_index<float>(h, h->poses[s], (const float*)dp[s], n[s], row_stride, h->offs[s])
+                           : launch_index<double>(h, h->poses[s], (const double*)dp[s], n[s], row_stride, h->offs[s]);
+    if (rc) return rc;
+  }
+  if (!is_device_ptr) {
+    CK(cudaEventRecord(h->in_free[h->in_sel ^ 1], h->stream));
+    CK(cudaEventSynchronize(h->copy_done));      // caller may reuse its host buffers on return
+  }
+  if (stage_mark(h, 1)) return EMAP_ERR_CUDA;
+  h->phase = 1;
+  return 0;
+}
+
+int frame_fuse(emap_handle* h) {
+  k_drift<<<1, 32, 0, h->stream>>>(h->dc, h->fs, h->pos_noise, h->ori_noise);
+  LAUNCH_CHECK();
+  if (stage_mark(h, 2)) return EMAP_ERR_CUDA;
+  if (h->n_points > 0) {
+    k_fuse<<<cdiv(h->n_points, 256), 256, 0, h->stream>>>(h->dc, h->n_points, h->global_off, h->xyzv, h->pidx, h->map,
+                                                            h->sc, h->fs);
+    LAUNCH_CHECK();
+  }
+  if (stage_mark(h, 3)) return EMAP_ERR_CUDA;
+  h->phase = 2;
+  return 0;
+}
+
+int frame_rays(emap_handle* h) {
+  if (h->dc.visibility) {
+    k_record<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs);
+    LAUNCH_CHECK();
+    if (stage_mark(h, 4)) return EMAP_ERR_CUDA;
+    const size_t sm = sizeof(float) * (size_t)h->dc.n_steps;
+    for (size_t s = 0; s + 1 < h->offs.size(); s++) {
+      const i64 n = h->offs[s + 1] - h->offs[s];
+      if (n <= 0) continue;
+      k_raycast<<<cdiv(n, 128), 128, sm, h->stream>>>(h->dc, h->poses[s], n, h->xyzv + h->offs[s], h->pidx + h->offs[s],
+                                                       h->normal, h->sc, h->steps, h->fs, h->count_rays);
+      LAUNCH_CHECK();
+    }
+  } else if (stage_mark(h, 4)) return EMAP_ERR_CUDA;
+  if (stage_mark(h, 5)) return EMAP_ERR_CUDA;
+  h->phase = 3;
+  return 0;
+}
+
+size_t post_smem(const DevCfg& d) {
+  const int HL = d.dilation + 3;
+  return sizeof(float) * (size_t)(2 * (PT_Y + 2 * HL) * (PT_X + 2 * HL) + (PT_Y + 6) * (PT_X + 6));
+}
+
+int launch_post(emap_handle* h) {
+  dim3 grid(cdiv(h->dc.W, PT_X), cdiv(h->dc.W, PT_Y));
+  k_post<<<grid, 256, post_smem(h->dc), h->stream>>>(h->dc, h->map, h->trav_input, h->normal);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int frame_finish(emap_handle* h) {
+  k_finalize<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs, h->dc.visibility);
+  LAUNCH_CHECK();
+  if (stage_mark(h, 6)) return EMAP_ERR_CUDA;
+  int rc = launch_post(h);
+  if (rc) return rc;
+  if (stage_mark(h, 7)) return EMAP_ERR_CUDA;
+  h->st.have = h->timing != 0;
+  h->phase = 0;
+  return 0;
+}
+
+int layer_index(const char* name) {
+  static const char* names[] = {"elevation", "variance", "is_valid", "traversability", "time", "upper_bound", "is_upper_bound"};
+  for (int i = 0; i < 7; i++) if (!strcmp(name, names[i])) return i;
+  return -1;
+}
+
+int alloc_plugin_scratch(emap_handle* h) {
+  for (int i = 0; i < 4; i++) if (!h->pl[i]) CK(cudaMalloc(&h->pl[i], sizeof(float) * h->dc.C));
+  return 0;
+}
+
+__global__ void k_ukey_extract(int C, const uint4* __restrict__ rec, int* __restrict__ x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) x[i] = (int)(rec[i].z ^ 0x80000000u);      // order-preserving u32 -> s32
+}
+__global__ void k_ukey_merge(int C, uint4* __restrict__ rec, const int* __restrict__ x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) rec[i].z = ((u32)x[i]) ^ 0x80000000u;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* emap_last_error(const emap_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int emap_create(const emap_config* cfg, int device, emap_handle** out) {
+  if (!cfg || !out) { g_create_error = "emap_create: null argument"; return EMAP_ERR_INVALID; }
+  if (cfg->abi_version != EMAP_ABI_VERSION) { g_create_error = "emap_create: abi_version mismatch"; return EMAP_ERR_INVALID; }
+  if (cfg->cell_n < 8 || cfg->cell_n > 2049) {
+    // beyond 2049 the reference's own clamp through float16 (CK.py:22-25,45-49) stops being exact
+    g_create_error = "emap_create: cell_n must be in [8, 2049]"; return EMAP_ERR_INVALID;
+  }
+  if (!(cfg->resolution > 0) || cfg->dilation_size < 0 || cfg->dilation_size > 8) {
+    g_create_error = "emap_create: resolution > 0 and 0 <= dilation_size <= 8 required"; return EMAP_ERR_INVALID;
+  }
+  emap_handle* h = new emap_handle();
+  h->cfg = *cfg; h->device = device;
+  auto bail = [&](const char* what, cudaError_t e) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+    emap_destroy(h);
+    return (int)EMAP_ERR_CUDA;
+  };
+  cudaError_t e;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  fill_devcfg(*cfg, h->dc);
+  build_steps(*cfg, h->dc.max_len16, h->steps_host);
+  h->dc.n_steps = (int)h->steps_host.size();
+  const size_t C = (size_t)h->dc.C;
+  if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  h->stream = h->own_stream;
+  if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  for (int b = 0; b < 2; b++) {
+    if ((e = cudaEventCreateWithFlags(&h->in_free[b], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    if ((e = cudaEventRecord(h->in_free[b], h->stream)) != cudaSuccess) return bail("event", e);
+  }
+  if ((e = cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+  for (int k = 0; k < 9; k++) if ((e = cudaEventCreate(&h->st.ev[k])) != cudaSuccess) return bail("event", e);
+#define ALLOC(p, bytes) if ((e = cudaMalloc(&(p), (bytes))) != cudaSuccess) return bail("cudaMalloc", e)
+  ALLOC(h->map, sizeof(float) * 7 * C);
+  ALLOC(h->map_alt, sizeof(float) * 7 * C);
+  ALLOC(h->normal, sizeof(float) * 3 * C);
+  ALLOC(h->trav_input, sizeof(float) * C);
+  ALLOC(h->u32_block, sizeof(u32) * 5 * C);
+  ALLOC(h->i64_block, sizeof(i64) * 3 * C);
+  ALLOC(h->sc.last, sizeof(u64) * C);
+  ALLOC(h->sc.rec, sizeof(uint4) * C);
+  ALLOC(h->ukey_x, sizeof(int) * C);
+  ALLOC(h->fs, sizeof(FrameScalars));
+  ALLOC(h->steps, sizeof(float) * (h->steps_host.size() + 1));
+  ALLOC(h->d_export, sizeof(float) * C);
+#undef ALLOC
+  h->sc.cnt_all = h->u32_block; h->sc.cnt_inl = h->u32_block + C; h->sc.cnt_fused = h->u32_block + 2 * C;
+  h->sc.n_out = h->u32_block + 3 * C; h->sc.n_ray = h->u32_block + 4 * C;
+  h->sc.SH = h->i64_block; h->sc.SV = h->i64_block + C; h->sc.DV = h->i64_block + 2 * C;
+  cudaMemsetAsync(h->u32_block, 0, sizeof(u32) * 5 * C, h->stream);
+  cudaMemsetAsync(h->i64_block, 0, sizeof(i64) * 3 * C, h->stream);
+  cudaMemsetAsync(h->sc.last, 0, sizeof(u64) * C, h->stream);
+  cudaMemsetAsync(h->sc.rec, 0, sizeof(uint4) * C, h->stream);
+  cudaMemsetAsync(h->normal, 0, sizeof(float) * 3 * C, h->stream);
+  cudaMemsetAsync(h->trav_input, 0, sizeof(float) * C, h->stream);
+  cudaMemsetAsync(h->fs, 0, sizeof(FrameScalars), h->stream);
+  if (!h->steps_host.empty())
+    cudaMemcpyAsync(h->steps, h->steps_host.data(), sizeof(float) * h->steps_host.size(), cudaMemcpyHostToDevice, h->stream);
+  k_init<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map);
+  h->launches++;
+  if (post_smem(h->dc) > 48 * 1024)
+    cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(h->dc));
+  if (sizeof(float) * h->steps_host.size() > 48 * 1024)
+    cudaFuncSetAttribute(k_raycast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * h->steps_host.size()));
+  if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail("init", e);
+  if ((e = cudaGetLastError()) != cudaSuccess) return bail("init", e);
+  *out = h;
+  return EMAP_OK;
+}
+
+int emap_destroy(emap_handle* h) {
+  if (!h) return EMAP_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  void* ptrs[] = {h->map, h->map_alt, h->normal, h->trav_input, h->u32_block, h->i64_block, h->sc.last, h->sc.rec,
+                  h->ukey_x, h->fs, h->steps, h->d_export, h->d_in[0], h->d_in[1], h->xyzv, h->pidx, h->pl[0], h->pl[1],
+                  h->pl[2], h->pl[3], h->pl_cnt};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (int b = 0; b < 2; b++) if (h->in_free[b]) cudaEventDestroy(h->in_free[b]);
+  if (h->copy_done) cudaEventDestroy(h->copy_done);
+  for (int k = 0; k < 9; k++) if (h->st.ev[k]) cudaEventDestroy(h->st.ev[k]);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+  return EMAP_OK;
+}
+
+#define ENTER(h)                                               \
+  if (!(h)) return EMAP_ERR_INVALID;                           \
+  std::lock_guard<std::mutex> lock_((h)->mu);                  \
+  {                                                            \
+    cudaError_t e_ = cudaSetDevice((h)->device);               \
+    if (e_ != cudaSuccess) { (h)->err = cudaGetErrorString(e_); return EMAP_ERR_CUDA; } \
+  }
+
+int emap_set_traversability_weights(emap_handle* h, const float* w1, const float* w2, const float* w3, const float* w_out) {
+  ENTER(h);
+  if (!w1 || !w2 || !w3 || !w_out) return fail(h, EMAP_ERR_INVALID, "null weights");
+  memcpy(h->dc.w1, w1, sizeof(float) * 36); memcpy(h->dc.w2, w2, sizeof(float) * 36);
+  memcpy(h->dc.w3, w3, sizeof(float) * 36); memcpy(h->dc.wout, w_out, sizeof(float) * 12);
+  return EMAP_OK;
+}
+
+int emap_input_sensors(emap_handle* h, int32_t n_sensors, const void* const* points, const int64_t* n, int64_t row_stride,
+                       int dtype, int is_device_ptr, const float* R, const float* t, float pn, float on) {
+  ENTER(h);
+  if (!points || !n || !R || !t) return fail(h, EMAP_ERR_INVALID, "emap_input: null argument");
+  int rc = frame_begin(h, n_sensors, points, n, row_stride, dtype, is_device_ptr, R, t, 0, pn, on);
+  if (rc) return rc;
+  if ((rc = frame_fuse(h))) return rc;
+  if ((rc = frame_rays(h))) return rc;
+  return frame_finish(h);
+}
+
+int emap_input_pointcloud(emap_handle* h, const void* points, int64_t n, int64_t row_stride, int dtype, int is_device_ptr,
+                          const float R[9], const float t[3], float pn, float on) {
+  const void* p[1] = {points};
+  int64_t nn[1] = {n};
+  return emap_input_sensors(h, 1, p, nn, row_stride, dtype, is_device_ptr, R, t, pn, on);
+}
+
+// ---- sharded frame ---------------------------------------------------------------------------
+
+int emap_shard_begin(emap_handle* h, int32_t n_sensors, const void* const* points, const int64_t* n, int64_t row_stride,
+                     int dtype, int is_device_ptr, const float* R, const float* t, int64_t global_point_offset, float pn,
+                     float on) {
+  ENTER(h);
+  if (!points || !n || !R || !t) return fail(h, EMAP_ERR_INVALID, "emap_shard_begin: null argument");
+  return frame_begin(h, n_sensors, points, n, row_stride, dtype, is_device_ptr, R, t, global_point_offset, pn, on);
+}
+
+int emap_shard_set_overlap_z(emap_handle* h, float z_abs) {
+  ENTER(h);
+  if (h->phase < 1) return fail(h, EMAP_ERR_STATE, "emap_shard_set_overlap_z must follow emap_shard_begin");
+  const float tz = z_abs - h->center[2];
+  CK(cudaMemcpyAsync(&h->fs->overlap_tz, &tz, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return EMAP_OK;
+}
+
+int emap_shard_exchange(emap_handle* h, int32_t phase, emap_exchange* out, int32_t* n_out) {
+  ENTER(h);
+  if (!out || !n_out || *n_out < 3) return fail(h, EMAP_ERR_INVALID, "emap_shard_exchange: need capacity >= 3");
+  const i64 C = h->dc.C;
+  if (phase == 1) {          // after begin: counts (CK.py:334,336) and the drift statistics (CK.py:332-333)
+    if (h->phase != 1) return fail(h, EMAP_ERR_STATE, "exchange 1 must follow emap_shard_begin");
+    out[0] = {h->sc.cnt_all, 2 * C, 3};
+    out[1] = {&h->fs->E, 2, 0};
+    *n_out = 2;
+  } else if (phase == 2) {   // after fusion: sums, counts, last-writer keys
+    if (h->phase != 2) return fail(h, EMAP_ERR_STATE, "exchange 2 must follow phase 1");
+    out[0] = {h->sc.SH, 2 * C, 0};
+    out[1] = {h->sc.cnt_fused, 2 * C, 3};
+    out[2] = {h->sc.last, C, 1};
+    *n_out = 3;
+  } else if (phase == 3) {   // after the ray-cast: decrements, counts, upper-bound keys
+    if (h->phase != 3) return fail(h, EMAP_ERR_STATE, "exchange 3 must follow phase 2");
+    if (h->dc.visibility) {
+      k_ukey_extract<<<cdiv(C, 256), 256, 0, h->stream>>>((int)C, h->sc.rec, h->ukey_x);
+      LAUNCH_CHECK();
+      out[0] = {h->sc.DV, C, 0};
+      out[1] = {h->sc.n_ray, C, 3};
+      out[2] = {h->ukey_x, C, 2};
+      *n_out = 3;
+      h->phase = 4;
+    } else *n_out = 0;
+  } else return fail(h, EMAP_ERR_INVALID, "emap_shard_exchange: phase must be 1..3");
+  return EMAP_OK;
+}
+
+int emap_shard_phase(emap_handle* h, int32_t phase) {
+  ENTER(h);
+  if (phase == 1) {
+    if (h->phase != 1) return fail(h, EMAP_ERR_STATE, "phase 1 must follow emap_shard_begin");
+    return frame_fuse(h);
+  }
+  if (phase == 2) {
+    if (h->phase != 2) return fail(h, EMAP_ERR_STATE, "phase 2 must follow phase 1");
+    return frame_rays(h);
+  }
+  if (phase == 3) {
+    if (h->phase != 3 && h->phase != 4) return fail(h, EMAP_ERR_STATE, "phase 3 must follow phase 2");
+    if (h->phase == 4) {
+      k_ukey_merge<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc.C, h->sc.rec, h->ukey_x);
+      LAUNCH_CHECK();
+    }
+    return frame_finish(h);
+  }
+  return fail(h, EMAP_ERR_INVALID, "emap_shard_phase: phase must be 1..3");
+}
+
+// ---- read-backs ------------------------------------------------------------------------------
+int emap_get_point_record(emap_handle* h, int32_t* idx, uint8_t* valid, uint8_t* inside, int64_t n) {
+  ENTER(h);
+  if (n > h->n_points) n = h->n_points;
+  std::vector<int> rec((size_t)(n > 0 ? n : 0));
+  if (n > 0) CK(cudaMemcpyAsync(rec.data(), h->pidx, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int64_t i = 0; i < n; i++) {
+    const int r = rec[i];
+    if (idx) idx[i] = (r & PT_SKIP) ? -1 : (r & PT_IDX_MASK);
+    if (valid) valid[i] = (r & PT_VALID) ? 1 : 0;
+    if (inside) inside[i] = (r & PT_INSIDE) ? 1 : 0;
+  }
+  return EMAP_OK;
+}
+
+int emap_get_frame_stats(emap_handle* h, emap_frame_stats* out) {
+  ENTER(h);
+  if (!out) return fail(h, EMAP_ERR_INVALID, "null out");
+  FrameScalars f;
+  CK(cudaMemcpyAsync(&f, h->fs, sizeof(f), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  out->mean_error = f.mean_error; out->additive_mean_error = f.additive_mean_error; out->shift_applied = f.shift;
+  out->error_sum = f.error_sum; out->error_cnt = f.ecnt; out->drift_applied = f.applied; out->drift_evaluated = f.evaluated;
+  out->n_points = h->n_points; out->n_valid_points = f.nvalid; out->ray_steps = f.ray_steps; out->ray_visits = f.ray_visits;
+  return EMAP_OK;
+}
+
+int emap_set_ray_counting(emap_handle* h, int enable) { ENTER(h); h->count_rays = enable ? 1 : 0; return EMAP_OK; }
+
+// ---- pose / time -----------------------------------------------------------------------------
+static int shift_map(emap_handle* h, int sx, int sy, double dz) {
+  const int nb = cdiv(h->dc.C, 256);
+  if (sx == 0 && sy == 0) {                                    // EM.py:208-209 early return, then shift_map_z
+    k_shift_z<<<nb, 256, 0, h->stream>>>(h->dc, h->map, dz);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  k_shift<<<dim3(nb, 7), 256, 0, h->stream>>>(h->dc, h->map, h->map_alt, sx, sy, dz);
+  LAUNCH_CHECK();
+  float* t = h->map; h->map = h->map_alt; h->map_alt = t;
+  return 0;
+}
+
+int emap_move_to(emap_handle* h, const double position[3], const float R[9]) {
+  ENTER(h);
+  if (!position) return fail(h, EMAP_ERR_INVALID, "null position");
+  if (R) memcpy(h->base_rotation, R, sizeof(float) * 9);       // EM.py:162
+  double delta[3];
+  for (int k = 0; k < 3; k++) delta[k] = position[k] - (double)h->center[k];      // EM.py:164
+  const double px = std::nearbyint(delta[0] / h->cfg.resolution), py = std::nearbyint(delta[1] / h->cfg.resolution);
+  h->center[0] = (float)((double)h->center[0] + px * h->cfg.resolution);          // EM.py:165-168
+  h->center[1] = (float)((double)h->center[1] + py * h->cfg.resolution);
+  h->center[2] = (float)((double)h->center[2] + delta[2]);
+  return shift_map(h, -(int)px, -(int)py, -delta[2]);                              // EM.py:169-170
+}
+
+int emap_move(emap_handle* h, const double d[3]) {
+  ENTER(h);
+  if (!d) return fail(h, EMAP_ERR_INVALID, "null delta");
+  const double px = std::nearbyint(d[0] / h->cfg.resolution), py = std::nearbyint(d[1] / h->cfg.resolution);   // EM.py:147
+  h->center[0] = (float)((double)h->center[0] + px * h->cfg.resolution);
+  h->center[1] = (float)((double)h->center[1] + py * h->cfg.resolution);
+  h->center[2] = (float)((double)h->center[2] + d[2]);
+  return shift_map(h, (int)px, (int)py, -d[2]);                                    // EM.py:151-152
+}
+
+int emap_clear(emap_handle* h) {
+  ENTER(h);
+  k_clear<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map);
+  LAUNCH_CHECK();
+  CK(cudaMemsetAsync(&h->fs->mean_error, 0, 2 * sizeof(float), h->stream));     // EM.py:127-128
+  return EMAP_OK;
+}
+
+int emap_update_variance(emap_handle* h) {
+  ENTER(h);
+  k_update_variance<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map);
+  LAUNCH_CHECK();
+  return EMAP_OK;
+}
+
+int emap_update_time(emap_handle* h) {
+  ENTER(h);
+  k_update_time<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map);
+  LAUNCH_CHECK();
+  return EMAP_OK;
+}
+
+int emap_update_normal(emap_handle* h, const float* dilated) {
+  ENTER(h);
+  k_normal<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, dilated ? dilated : h->trav_input, h->map + 2 * (size_t)h->dc.C, h->normal);
+  LAUNCH_CHECK();
+  return EMAP_OK;
+}
+
+int emap_get_position(emap_handle* h, double out[3]) {
+  ENTER(h);
+  for (int k = 0; k < 3; k++) out[k] = h->center[k];
+  return EMAP_OK;
+}
+
+// ---- export ----------------------------------------------------------------------------------
+int emap_get_map_with_name(emap_handle* h, const char* name, float* out_host, int64_t n_out) {
+  ENTER(h);
+  if (!name || !out_host) return fail(h, EMAP_ERR_INVALID, "null argument");
+  static const char* names[] = {"elevation", "variance", "traversability", "time", "upper_bound", "is_upper_bound",
+                                "normal_x", "normal_y", "normal_z"};
+  int kind = -1;
+  for (int i = 0; i < 9; i++) if (!strcmp(name, names[i])) kind = i;
+  if (kind < 0) { h->err = std::string("Layer ") + name + " is not in the map"; return EMAP_ERR_NOLAYER; }
+  const int Wo = h->dc.W - 2;
+  if (n_out != (int64_t)Wo * Wo) return fail(h, EMAP_ERR_INVALID, "output must hold (cell_n-2)^2 floats");
+  k_export<<<cdiv((i64)Wo * Wo, 256), 256, 0, h->stream>>>(h->dc, h->map, h->normal, h->d_export, kind, h->center[2],
+                                                              h->cfg.use_only_above_for_upper_bound, nullptr, 0);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(out_host, h->d_export, sizeof(float) * Wo * Wo, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return EMAP_OK;
+}
+
+int emap_export_plane(emap_handle* h, const float* plane, int fill_nan, int add_z, float* out_host, int64_t n_out) {
+  ENTER(h);
+  if (!plane || !out_host) return fail(h, EMAP_ERR_INVALID, "null argument");
+  const int Wo = h->dc.W - 2;
+  if (n_out != (int64_t)Wo * Wo) return fail(h, EMAP_ERR_INVALID, "output must hold (cell_n-2)^2 floats");
+  k_export<<<cdiv((i64)Wo * Wo, 256), 256, 0, h->stream>>>(h->dc, h->map, h->normal, h->d_export, 9, h->center[2], 0, plane,
+                                                              (fill_nan ? 1 : 0) | (add_z ? 2 : 0));
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(out_host, h->d_export, sizeof(float) * Wo * Wo, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return EMAP_OK;
+}
+
+int emap_layer_device_ptr(emap_handle* h, const char* name, void** ptr) {
+  ENTER(h);
+  if (!name || !ptr) return fail(h, EMAP_ERR_INVALID, "null argument");
+  const size_t C = (size_t)h->dc.C;
+  int li = layer_index(name);
+  if (li >= 0) { *ptr = h->map + li * C; return EMAP_OK; }
+  if (!strcmp(name, "elevation_map")) { *ptr = h->map; return EMAP_OK; }
+  if (!strcmp(name, "normal_map") || !strcmp(name, "normal_x")) { *ptr = h->normal; return EMAP_OK; }
+  if (!strcmp(name, "normal_y")) { *ptr = h->normal + C; return EMAP_OK; }
+  if (!strcmp(name, "normal_z")) { *ptr = h->normal + 2 * C; return EMAP_OK; }
+  if (!strcmp(name, "traversability_input")) { *ptr = h->trav_input; return EMAP_OK; }
+  h->err = std::string("Layer ") + name + " is not in the map";
+  return EMAP_ERR_NOLAYER;
+}
+
+int emap_exists_layer(const emap_handle* h, const char* name) {
+  if (!h || !name) return 0;
+  return layer_index(name) >= 0 ? 1 : 0;
+}
+
+int emap_get_state(emap_handle* h, float* map_host, float* normal_host) {
+  ENTER(h);
+  const size_t C = (size_t)h->dc.C;
+  if (map_host) CK(cudaMemcpyAsync(map_host, h->map, sizeof(float) * 7 * C, cudaMemcpyDeviceToHost, h->stream));
+  if (normal_host) CK(cudaMemcpyAsync(normal_host, h->normal, sizeof(float) * 3 * C, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return EMAP_OK;
+}
+
+int emap_set_state(emap_handle* h, const float* map_host, const float* normal_host, const double center[3]) {
+  ENTER(h);
+  const size_t C = (size_t)h->dc.C;
+  if (map_host) CK(cudaMemcpyAsync(h->map, map_host, sizeof(float) * 7 * C, cudaMemcpyHostToDevice, h->stream));
+  if (normal_host) CK(cudaMemcpyAsync(h->normal, normal_host, sizeof(float) * 3 * C, cudaMemcpyHostToDevice, h->stream));
+  if (center) for (int k = 0; k < 3; k++) h->center[k] = (float)center[k];
+  CK(cudaStreamSynchronize(h->stream));
+  return EMAP_OK;
+}
+
+// ---- plugins ---------------------------------------------------------------------------------
+int emap_min_filter(emap_handle* h, const float* elevation, const float* is_valid, float* out, int32_t k, int32_t iteration_n,
+                    int32_t* iterations_run) {
+  ENTER(h);
+  if (!elevation || !is_valid || !out || k < 0 || k > 16 || iteration_n < 1)
+    return fail(h, EMAP_ERR_INVALID, "emap_min_filter: bad argument");
+  int rc = alloc_plugin_scratch(h);
+  if (rc) return rc;
+  if (h->pl_cnt_cap < iteration_n + 1) {
+    if (h->pl_cnt) cudaFree(h->pl_cnt);
+    h->pl_cnt = nullptr; h->pl_cnt_cap = 0;
+    CK(cudaMalloc(&h->pl_cnt, sizeof(int) * (iteration_n + 1)));
+    h->pl_cnt_cap = iteration_n + 1;
+  }
+  const size_t B = sizeof(float) * (size_t)h->dc.C;
+  float *hA = h->pl[0], *mA = h->pl[1], *hB = h->pl[2], *mB = h->pl[3];
+  CK(cudaMemsetAsync(h->pl_cnt, 0, sizeof(int) * (iteration_n + 1), h->stream));
+  CK(cudaMemcpyAsync(hA, elevation, B, cudaMemcpyDeviceToDevice, h->stream));      // min_filter.py:105-106
+  CK(cudaMemcpyAsync(mA, is_valid, B, cudaMemcpyDeviceToDevice, h->stream));
+  const int nb = cdiv(h->dc.C, 256);
+  for (int it = 0; it < iteration_n; it++) {
+    const bool even = (it & 1) == 0;
+    k_min_filter_iter<<<nb, 256, 0, h->stream>>>(h->dc, k, is_valid, even ? hA : hB, even ? mA : mB, even ? hB : hA,
+                                                  even ? mB : mA, h->pl_cnt, it);
+    LAUNCH_CHECK();
+  }
+  k_min_filter_final<<<nb, 256, 0, h->stream>>>(h->dc, hA, mA, hB, mB, h->pl_cnt, iteration_n, out, h->pl_cnt + iteration_n);
+  LAUNCH_CHECK();
+  if (iterations_run) {
+    CK(cudaMemcpyAsync(iterations_run, h->pl_cnt + iteration_n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return EMAP_OK;
+}
+
+int emap_smooth_filter(emap_handle* h, const float* in, float* out) {
+  ENTER(h);
+  if (!in || !out) return fail(h, EMAP_ERR_INVALID, "null argument");
+  int rc = alloc_plugin_scratch(h);
+  if (rc) return rc;
+  const int nb = cdiv(h->dc.C, 256);
+  k_box3<<<nb, 256, 0, h->stream>>>(h->dc, in, h->pl[0], 0); LAUNCH_CHECK();
+  k_box3<<<nb, 256, 0, h->stream>>>(h->dc, h->pl[0], h->pl[1], 1); LAUNCH_CHECK();
+  k_box3<<<nb, 256, 0, h->stream>>>(h->dc, h->pl[1], h->pl[0], 0); LAUNCH_CHECK();
+  k_box3<<<nb, 256, 0, h->stream>>>(h->dc, h->pl[0], out, 1); LAUNCH_CHECK();
+  return EMAP_OK;
+}
+
+int emap_inpaint(emap_handle* h, const float*, const float*, float*, int32_t) {
+  return fail(h, EMAP_ERR_INVALID, "emap_inpaint: not implemented in this build");
+}
+
+// ---- plumbing --------------------------------------------------------------------------------
+int emap_sync(emap_handle* h) {
+  ENTER(h);
+  CK(cudaStreamSynchronize(h->stream));
+  return EMAP_OK;
+}
+
+int emap_stream(emap_handle* h, void** s) { if (!h || !s) return EMAP_ERR_INVALID; *s = (void*)h->stream; return EMAP_OK; }
+int emap_set_stream(emap_handle* h, void* s) {
+  ENTER(h);
+  CK(cudaStreamSynchronize(h->stream));
+  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return EMAP_OK;
+}
+int emap_cell_n(const emap_handle* h) { return h ? h->dc.W : EMAP_ERR_INVALID; }
+int64_t emap_launch_count(const emap_handle* h) { return h ? h->launches : 0; }
+
+int emap_enable_stage_timing(emap_handle* h, int enable) { ENTER(h); h->timing = enable ? 1 : 0; h->st.have = false; return EMAP_OK; }
+
+int emap_get_stage_ms(emap_handle* h, float out[8]) {
+  ENTER(h);
+  if (!out) return fail(h, EMAP_ERR_INVALID, "null out");
+  if (!h->st.have) return fail(h, EMAP_ERR_STATE, "no timed frame (emap_enable_stage_timing first)");
+  CK(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < 7; k++) CK(cudaEventElapsedTime(&out[k], h->st.ev[k], h->st.ev[k + 1]));
+  CK(cudaEventElapsedTime(&out[7], h->st.ev[0], h->st.ev[7]));
+  return EMAP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,580 @@
+// emap_kernels.cuh -- the per-frame kernels of the fusion path (sm_100a).
+//
+// Frame = elevation_mapping.py:316-391 (update_map_with_kernel) executed under the canonical
+// serialisation of SURVEY.md 8(c):
+//   k_index_error   CK.py:280-345   per point: geometry, cell, drift-inlier statistics, counts
+//   k_drift         EM.py:346-357   one thread: mean error, shift decision (no host sync)
+//   k_fuse          CK.py:168-197   per point: Kalman update against the pre-frame snapshot
+//   k_record        --              per cell: pack the post-fusion state a ray needs into 16 B
+//   k_raycast       CK.py:198-259   per point: visibility cleanup / upper-bound carving
+//   k_finalize      CK.py:348-389 + EM.py:393-410   per cell: apply all side effects, average, overlap clear
+//   k_post          CK.py:392-449, traversability_filter.py:15-42, CK.py:452-506  dilation + CNN + normals
+// Order-dependent float accumulations of the reference (atomicAdd of new_h, new_v, validity
+// decrements, drift errors) are accumulated exactly in 2^-32 fixed point (int64 atomics), which
+// makes every result independent of thread order, run-to-run deterministic and bit-identical to
+// oracle/emap_oracle.c; they are within one fp32 rounding of some order of the reference atomics.
+#pragma once
+#include "emap_device.cuh"
+
+// ------------------------------------------------------------------------------------------
+// per-cell scratch of a frame; all zero between frames (k_finalize re-zeroes what it consumed)
+struct CellScratch {
+  u32* cnt_all;    // newmap[4]  CK.py:336
+  u32* cnt_inl;    // newmap[3]  CK.py:334
+  u32* cnt_fused;  // newmap[2]  CK.py:185
+  u32* n_out;      // number of atomicAdd(map[1], outlier_variance) by outlier points, CK.py:174
+  u32* n_ray;      // ... by penetrating rays, CK.py:251
+  i64* SH;         // sum new_h   CK.py:183
+  i64* SV;         // sum new_v   CK.py:184
+  i64* DV;         // sum of validity decrements CK.py:250
+  u64* last;       // (global point index << 32 | bits(new_h)) max  -> upper_bound of a hit cell, CK.py:191
+  uint4* rec;      // ray record {h', v', ukey, flags}
+};
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64 n, const i64 stride,
+              float4* __restrict__ xyzv, int* __restrict__ pidx, const float* __restrict__ map,
+              u32* __restrict__ cnt_all, u32* __restrict__ cnt_inl, FrameScalars* fs) {
+  const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  i64 e = 0; int ec = 0, nv = 0;
+  if (i < n) {
+    const T* p = pts + i * stride;
+    float px = (float)p[0], py = (float)p[1], pz = (float)p[2];   // EM.py:456 cast to fp32
+    int rec;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (px != px || py != py || pz != pz) {                       // EM.py:458 drop NaN rows
+      rec = PT_SKIP | PT_IDX_MASK;
+    } else {
+      Geom g; point_geom(c, q, px, py, pz, g);
+      const int idx = g.ix * c.W + g.iy;
+      rec = idx | (g.valid ? PT_VALID : 0) | (g.inside ? PT_INSIDE : 0);
+      o = make_float4(g.x, g.y, g.z, g.v);
+      nv = g.valid;
+      if (g.valid && g.inside) {                                  // CK.py:318-323
+        const float mh = __ldg(map + idx), mv = __ldg(map + c.C + idx);
+        const float mvalid = __ldg(map + 2 * c.C + idx), mt = __ldg(map + 3 * c.C + idx);
+        if (mvalid > 0.5f && (double)fabsf(mh - g.z) < (double)mv * c.mahal
+            && (double)mv < c.inlier_var_half && (double)mt > c.trav_inlier) {   // CK.py:328-330
+          e = fix32(g.z - mh); ec = 1;
+          atomicAdd(cnt_inl + idx, 1u);
+        }
+        atomicAdd(cnt_all + idx, 1u);
+      }
+    }
+    xyzv[i] = o; pidx[i] = rec;
+  }
+  // block reduction -> one integer atomic per block (order independent)
+  for (int o = 16; o > 0; o >>= 1) {
+    e += __shfl_down_sync(0xffffffffu, e, o);
+    ec += __shfl_down_sync(0xffffffffu, ec, o);
+    nv += __shfl_down_sync(0xffffffffu, nv, o);
+  }
+  __shared__ i64 s_e[8]; __shared__ int s_c[8], s_v[8];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_e[w] = e; s_c[w] = ec; s_v[w] = nv; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; k++) { e += s_e[k]; ec += s_c[k]; nv += s_v[k]; }
+    if (e != 0) atomicAdd((u64*)&fs->E, (u64)e);
+    if (ec) atomicAdd((u64*)&fs->ecnt, (u64)ec);
+    if (nv) atomicAdd((u64*)&fs->nvalid, (u64)nv);
+  }
+}
+
+// EM.py:346-357
+__global__ void k_drift(const DevCfg c, FrameScalars* fs, float position_noise, float orientation_noise) {
+  if (threadIdx.x || blockIdx.x) return;
+  const i64 ecnt = fs->ecnt;
+  const float error_sum = (float)unfix32(fs->E);
+  fs->error_sum = error_sum; fs->shift = 0.f; fs->applied = 0; fs->evaluated = 0;
+  if (c.drift_en && (double)(float)ecnt > c.min_drift_cnt
+      && ((double)position_noise > c.pos_thresh || (double)orientation_noise > c.ori_thresh)) {
+    const float mean = __fdiv_rn(error_sum, (float)ecnt);
+    fs->mean_error = mean; fs->evaluated = 1;
+    fs->additive_mean_error = __fadd_rn(fs->additive_mean_error, mean);
+    if (fabsf(mean) < c.max_drift_f) { fs->shift = __fmul_rn(mean, c.drift_alpha_f); fs->applied = 1; }
+  }
+}
+
+// CK.py:168-197 fusion half; every load is of the pre-frame snapshot (+ drift shift)
+__global__ void __launch_bounds__(256)
+k_fuse(const DevCfg c, const i64 n, const i64 global_off, const float4* __restrict__ xyzv,
+       const int* __restrict__ pidx, const float* __restrict__ map, const CellScratch s,
+       const FrameScalars* __restrict__ fs) {
+  const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int rec = pidx[i];
+  if ((rec & (PT_VALID | PT_INSIDE | PT_SKIP)) != (PT_VALID | PT_INSIDE)) return;
+  const int idx = rec & PT_IDX_MASK;
+  const float4 g = xyzv[i];
+  const float z = g.z, v = g.w;
+  float mh = __ldg(map + idx);
+  if (fs->applied) mh = __fadd_rn(mh, fs->shift);                 // EM.py:357 applied lazily
+  const float mv = __ldg(map + c.C + idx);
+  const float num_points = (float)s.cnt_all[idx];                 // CK.py:172
+  if ((double)fabsf(mh - z) > (double)mv * c.mahal) {
+    atomicAdd(s.n_out + idx, 1u);                                 // CK.py:174
+  } else if (c.edge_sharpen && (double)num_points > c.wall_thresh
+             && (double)z < (double)mh - (double)mv * c.mahal / (double)num_points) {
+    // CK.py:177-179 edge sharpening: skip
+  } else {
+    const float den = __fadd_rn(mv, v);
+    const float new_h = __fdiv_rn(__fmaf_rn(mh, v, __fmul_rn(z, mv)), den);   // CK.py:181 (nvcc contraction)
+    const float new_v = __fdiv_rn(__fmul_rn(mv, v), den);                     // CK.py:182
+    atomicAdd((u64*)(s.SH + idx), (u64)fix32(new_h));
+    atomicAdd((u64*)(s.SV + idx), (u64)fix32(new_v));
+    atomicAdd(s.cnt_fused + idx, 1u);
+    atomicMax(s.last + idx, ((u64)(u32)(global_off + i) << 32) | (u64)__float_as_uint(new_h));
+  }
+}
+
+// n sequential fp32 additions of the constant c (the atomicAdds of CK.py:174 / CK.py:251)
+__device__ __forceinline__ float add_n_times(float v, float c, u32 n) {
+  for (u32 k = 0; k < n; k++) v = __fadd_rn(v, c);
+  return v;
+}
+
+// post-fusion state of a cell as a ray sees it (SURVEY 8(c) step 3 -> 4), packed to 16 B
+__global__ void __launch_bounds__(256)
+k_record(const DevCfg c, const float* __restrict__ map, const CellScratch s, const FrameScalars* __restrict__ fs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.C) return;
+  float h = map[i];
+  if (fs->applied) h = __fadd_rn(h, fs->shift);
+  float v = add_n_times(map[c.C + i], c.c_out, s.n_out[i]);
+  float valid = map[2 * c.C + i], time = map[4 * c.C + i];
+  float upper = map[5 * c.C + i], isup = map[6 * c.C + i];
+  u32 ukey;
+  if (s.cnt_fused[i] > 0) { valid = 1.f; time = 0.f; ukey = UKEY_NONE; }   // CK.py:187-192
+  else ukey = (isup < 0.5f) ? UKEY_NONE : fkey(upper);
+  u32 fl = (valid < 0.5f ? 0u : RF_VALID) | (time < 0.5f ? RF_T05 : 0u) | ((double)time < 1.0 ? RF_T10 : 0u)
+         | ((double)(float)s.cnt_inl[i] > c.wall_thresh ? RF_WALL : 0u);
+  s.rec[i] = make_uint4(__float_as_uint(h), __float_as_uint(v), ukey, fl);
+}
+
+// CK.py:198-259 ray-cast half: one thread per valid point.  `steps` is the shared table of the
+// fp16 march variable s_k (s_0 = half(step), s_{k+1} = half(float(double(s_k) + step)), CK.py:203).
+__global__ void __launch_bounds__(128)
+k_raycast(const DevCfg c, const Pose q, const i64 n, const float4* __restrict__ xyzv,
+          const int* __restrict__ pidx, const float* __restrict__ normal, const CellScratch s,
+          const float* __restrict__ steps, FrameScalars* fs, const int count) {
+  extern __shared__ float s_steps[];
+  for (int k = threadIdx.x; k < c.n_steps; k += blockDim.x) s_steps[k] = steps[k];
+  __syncthreads();
+  const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int prec = pidx[i];
+  if ((prec & (PT_VALID | PT_SKIP)) != PT_VALID) return;          // CK.py:226: invalid points do nothing
+  const float4 g = xyzv[i];
+  const float x = g.x, y = g.y, z = g.z;
+  // ray_vector CK.py:83-101
+  const float vx = h16(h16(x) - q.t16[0]), vy = h16(h16(y) - q.t16[1]), vz = h16(h16(z) - q.t16[2]);
+  const float norm = h16(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz))));
+  float rx = 0.f, ry = 0.f, rz = 0.f;
+  if (norm > 0.f) { rx = h16(__fdiv_rn(vx, norm)); ry = h16(__fdiv_rn(vy, norm)); rz = h16(__fdiv_rn(vz, norm)); }
+  const float len = fminf(norm, c.max_len16);                     // CK.py:201
+  const float dec = (float)(-c.cleanup_step / ((double)len / c.max_ray_length));   // CK.py:250
+  const i64 dec_fix = fix32(dec);
+  const int W = c.W;
+  int last_idx = -1;
+  int n_steps_done = 0, n_visits = 0;
+  for (int k = 0; k < c.n_steps; k++) {
+    const float sk = s_steps[k];
+    if (!(sk < len)) break;
+    n_steps_done++;
+    const float nx = __fmaf_rn(rx, sk, q.t[0]);                   // t + ray*s: product exact (CK.py:205-207)
+    const float ny = __fmaf_rn(ry, sk, q.t[1]);
+    const int ix = axis_cell(c, h16(nx)), iy = axis_cell(c, h16(ny));
+    const int nidx = ix * W + iy;
+    if (nidx == last_idx) continue;                               // CK.py:209
+    last_idx = nidx;
+    if (!cell_inside(W, ix, iy)) continue;                        // CK.py:211
+    const float nz = __fmaf_rn(rz, sk, q.t[2]);
+    const float ddx = x - nx, ddy = y - ny, ddz = z - nz;
+    float d = __fmul_rn(ddy, ddy); d = __fmaf_rn(ddx, ddx, d); d = __fmaf_rn(ddz, ddz, d);   // CK.py:225
+    d = h16(d);
+    if ((double)d < 0.1) continue;                                // CK.py:226
+    n_visits++;
+    const uint4 r = s.rec[nidx];
+    if (!(r.w & RF_VALID)) {                                      // CK.py:229-235 carve the upper bound
+      const u32 key = fkey(nz);
+      if (key < r.z) atomicMin(&s.rec[nidx].z, key);
+      continue;
+    }
+    if (r.w & RF_T05) continue;                                   // CK.py:237
+    const float nh = __uint_as_float(r.x), nv = __uint_as_float(r.y);
+    const double rhs = fma(-fmin((double)nv, 1.0), 0.05, (double)nz + 0.01);   // CK.py:239 (nvcc contraction)
+    if ((double)nh > rhs) {
+      const float n0 = h16(__ldg(normal + nidx)), n1 = h16(__ldg(normal + c.C + nidx)), n2 = h16(__ldg(normal + 2 * c.C + nidx));
+      const float product = __fadd_rn(__fadd_rn(__fmul_rn(rx, n0), __fmul_rn(ry, n1)), __fmul_rn(rz, n2));   // CK.py:103-108
+      if ((double)fabsf(product) < c.cos_thresh) continue;        // CK.py:245
+      if ((r.w & RF_WALL) && (r.w & RF_T10)) continue;            // CK.py:246-247
+      atomicAdd((u64*)(s.DV + nidx), (u64)dec_fix);               // CK.py:250
+      atomicAdd(s.n_ray + nidx, 1u);                              // CK.py:251
+      const u32 key = fkey(nz);                                   // CK.py:253-256
+      if (key < r.z) atomicMin(&s.rec[nidx].z, key);
+    }
+  }
+  if (count) {
+    for (int o = 16; o > 0; o >>= 1) {
+      n_steps_done += __shfl_down_sync(0xffffffffu, n_steps_done, o);
+      n_visits += __shfl_down_sync(0xffffffffu, n_visits, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd((u64*)&fs->ray_steps, (u64)n_steps_done);
+      atomicAdd((u64*)&fs->ray_visits, (u64)n_visits);
+    }
+  }
+}
+
+// Apply every side effect of the frame to the state planes, then average_map_kernel
+// (CK.py:362-384) and clear_overlap_map (EM.py:393-410); re-zero the consumed scratch.
+__global__ void __launch_bounds__(256)
+k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const FrameScalars* __restrict__ fs,
+           const int rays_ran) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.C) return;
+  const int C = c.C;
+  const u32 cf = s.cnt_fused[i], no = s.n_out[i], ca = s.cnt_all[i];
+  const u32 nr = rays_ran ? s.n_ray[i] : 0u;
+  const u32 ukey = rays_ran ? s.rec[i].z : 0u;
+  const int applied = fs->applied;
+  const int r = i / c.W, col = i - r * c.W;
+  const bool in_win = c.overlap && r >= c.cell_min && r < c.cell_max && col >= c.cell_min && col < c.cell_max;
+  float h0 = map[i], v0 = map[C + i], valid0 = map[2 * C + i];
+  float time0 = map[4 * C + i], upper0 = map[5 * C + i], isup0 = map[6 * C + i];
+  float h = h0, v = v0, valid = valid0, time = time0, upper = upper0, isup = isup0;
+  if (applied) h = __fadd_rn(h, fs->shift);
+  v = add_n_times(v, c.c_out, no);
+  if (cf > 0) {                                                   // CK.py:187-192
+    valid = 1.f; time = 0.f; isup = 0.f;
+    upper = __uint_as_float((u32)(s.last[i] & 0xffffffffull));
+  }
+  if (rays_ran) {
+    const u32 key0 = (isup < 0.5f) ? UKEY_NONE : fkey(upper);
+    if (nr > 0) {
+      valid = __fadd_rn(valid, (float)unfix32(s.DV[i]));          // CK.py:250
+      v = add_n_times(v, c.c_out, nr);                            // CK.py:251
+    }
+    if (ukey != key0) { upper = funkey(ukey); isup = 1.f; }       // CK.py:230-233,253-256 (true min over rays)
+  }
+  // average_map_kernel CK.py:362-384
+  const float valid_in = valid;
+  if (cf > 0) {
+    const double cnt = (double)cf;
+    const float mean_v = (float)(unfix32(s.SV[i]) / cnt);
+    if ((double)mean_v > c.max_variance) { h = 0.f; v = c.init_var; valid = 0.f; }
+    else { h = (float)(unfix32(s.SH[i]) / cnt); v = mean_v; valid = 1.f; }
+  }
+  if (valid_in < 0.5f) { h = 0.f; v = c.init_var; valid = 0.f; }
+  // clear_overlap_map EM.py:393-410
+  if (in_win) {
+    const float hmin = __fsub_rn(fs->overlap_tz, c.overlap_z_f), hmax = __fadd_rn(fs->overlap_tz, c.overlap_z_f);
+    if (h < hmin || h > hmax) { h = 0.f; v = c.init_var; valid = 0.f; }
+    if (upper < hmin || upper > hmax) { upper = 0.f; isup = 0.f; }
+  }
+  if (h != h0 || applied) map[i] = h;
+  if (v != v0) map[C + i] = v;
+  if (valid != valid0) map[2 * C + i] = valid;
+  if (time != time0) map[4 * C + i] = time;
+  if (upper != upper0) map[5 * C + i] = upper;
+  if (isup != isup0) map[6 * C + i] = isup;
+  // re-zero scratch
+  if (ca) { s.cnt_all[i] = 0; s.cnt_inl[i] = 0; }
+  if (no) s.n_out[i] = 0;
+  if (cf) { s.cnt_fused[i] = 0; s.SH[i] = 0; s.SV[i] = 0; s.last[i] = 0; }
+  if (nr) { s.n_ray[i] = 0; s.DV[i] = 0; }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_post: dilation (CK.py:392-449) of upper_bound with mask = is_valid + is_upper_bound
+// (EM.py:376-383) -> traversability_input; traversability CNN (traversability_filter.py:15-42)
+// -> map[3][3:-3,3:-3] (EM.py:385-388); normals of the dilated map (CK.py:452-506, EM.py:564-577).
+// One CTA per PT_Y x PT_X tile; the (tile + halo) of the two input planes is staged in shared
+// memory once, the dilated tile (+3 halo) stays in shared memory for the CNN and the normals.
+#define PT_X 32
+#define PT_Y 16
+
+// exact flat-index semantics of CK.py:403-418,429-438 for one cell, from global memory
+__device__ float dilate_cell_global(const DevCfg& c, const float* __restrict__ up, const float* __restrict__ valid,
+                                    const float* __restrict__ isup, int i) {
+  const int W = c.W, k = c.dilation;
+  const float h = up[i];
+  if (__fadd_rn(valid[i], isup[i]) >= 0.5f) return h;
+  float distance = 100.f, near_value = 0.f;
+  for (int dy = -k; dy <= k; dy++)
+    for (int dx = -k; dx <= k; dx++) {
+      const int idx = i + W * dy + dx;
+      const int ix = idx / W, iy = idx % W;                        // C division, as the reference
+      if (ix <= 0 || ix >= W - 1 || iy <= 0 || iy >= W - 1) continue;
+      if (idx < 0 || idx >= c.C) continue;
+      if (__fadd_rn(valid[idx], isup[idx]) > 0.5f && (float)(dx + dy) < distance) {
+        distance = (float)(dx + dy); near_value = up[idx];
+      }
+    }
+  return distance < 100.f ? near_value : h;
+}
+
+__global__ void __launch_bounds__(256)
+k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, float* __restrict__ normal) {
+  extern __shared__ float smem[];
+  const int W = c.W, C = c.C, k = c.dilation;
+  const int HL = k + 3;                          // halo of the staged inputs
+  const int A = PT_Y + 2 * HL, B = PT_X + 2 * HL;
+  const int DA = PT_Y + 6, DB = PT_X + 6;
+  float* s_up = smem;                            // A*B
+  float* s_mask = s_up + A * B;                  // A*B   is_valid + is_upper_bound
+  float* s_dil = s_mask + A * B;                 // DA*DB
+  const float* up = map + 5 * C; const float* valid = map + 2 * C; const float* isup = map + 6 * C;
+  const int r0 = blockIdx.y * PT_Y, c0 = blockIdx.x * PT_X;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < A * B; e += blockDim.x) {
+    const int a = e / B, b = e - a * B;
+    const int r = r0 - HL + a, cc = c0 - HL + b;
+    float u = 0.f, m = 0.f;
+    if (r >= 0 && r < W && cc >= 0 && cc < W) {
+      const int gi = r * W + cc;
+      u = __ldg(up + gi);
+      m = __fadd_rn(__ldg(valid + gi), __ldg(isup + gi));
+    }
+    s_up[e] = u; s_mask[e] = m;
+  }
+  __syncthreads();
+  for (int e = tid; e < DA * DB; e += blockDim.x) {
+    const int a = e / DB, b = e - a * DB;
+    const int r = r0 - 3 + a, cc = c0 - 3 + b;
+    float out = 0.f;
+    if (r >= 0 && r < W && cc >= 0 && cc < W) {
+      if (cc - k >= 0 && cc + k <= W - 1) {      // no row wrap-around possible: shared-memory path
+        const int sa = a + k, sb = b + k;        // position in the staged planes (HL - 3 == k)
+        out = s_up[sa * B + sb];
+        if (s_mask[sa * B + sb] < 0.5f) {
+          float distance = 100.f, near_value = 0.f;
+          for (int dy = -k; dy <= k; dy++) {
+            const int rr = r + dy;
+            if (rr <= 0 || rr >= W - 1) continue;
+            for (int dx = -k; dx <= k; dx++) {
+              const int c2 = cc + dx;
+              if (c2 <= 0 || c2 >= W - 1) continue;
+              if (s_mask[(sa + dy) * B + sb + dx] > 0.5f && (float)(dx + dy) < distance) {
+                distance = (float)(dx + dy); near_value = s_up[(sa + dy) * B + sb + dx];
+              }
+            }
+          }
+          if (distance < 100.f) out = near_value;
+        }
+      } else {
+        out = dilate_cell_global(c, up, valid, isup, r * W + cc);
+      }
+    }
+    s_dil[e] = out;
+  }
+  __syncthreads();
+  for (int e = tid; e < PT_Y * PT_X; e += blockDim.x) {
+    const int a = e / PT_X, b = e - a * PT_X;
+    const int r = r0 + a, cc = c0 + b;
+    if (r >= W || cc >= W) continue;
+    const int gi = r * W + cc;
+    const float* d = s_dil + (a + 3) * DB + (b + 3);
+    const float h = d[0];
+    trav_input[gi] = h;
+    // traversability CNN; summation order = oracle_traversability
+    if (r >= 3 && r <= W - 4 && cc >= 3 && cc <= W - 4) {
+      float acc = 0.f;
+#pragma unroll
+      for (int l = 0; l < 3; l++) {
+        const int dil = l + 1;
+        const float* wl = (l == 0) ? c.w1 : (l == 1) ? c.w2 : c.w3;
+        float t[9];
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+#pragma unroll
+          for (int qq = 0; qq < 3; qq++) t[p * 3 + qq] = d[(p - 1) * dil * DB + (qq - 1) * dil];
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 9; j++) sacc = __fmaf_rn(wl[ch * 9 + j], t[j], sacc);
+          acc = __fmaf_rn(c.wout[l * 4 + ch], fabsf(sacc), acc);
+        }
+      }
+      map[3 * C + gi] = expf(-acc);
+    }
+    // normals CK.py:486-501 (normal_map is cleared first, EM.py:571)
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+    if (__ldg(valid + gi) > 0.5f && r >= 1 && r <= W - 3 && cc >= 1 && cc <= W - 3) {
+      const float dzdx = __fsub_rn(d[1], h), dzdy = __fsub_rn(d[DB], h);
+      const float nx = __fdiv_rn(-dzdy, c.res_f), ny = __fdiv_rn(-dzdx, c.res_f);
+      const float nn = __fsqrt_rn(__fadd_rn(__fmaf_rn(nx, nx, __fmul_rn(ny, ny)), 1.0f));
+      n0 = __fdiv_rn(nx, nn); n1 = __fdiv_rn(ny, nn); n2 = __fdiv_rn(1.0f, nn);
+    }
+    normal[gi] = n0; normal[C + gi] = n1; normal[2 * C + gi] = n2;
+  }
+}
+
+// EM.py:564-577 update_normal(dilated_map) with an arbitrary device plane
+__global__ void __launch_bounds__(256)
+k_normal(const DevCfg c, const float* __restrict__ dil, const float* __restrict__ valid, float* __restrict__ normal) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.C) return;
+  const int W = c.W, r = i / W, cc = i - r * W;
+  float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+  if (valid[i] > 0.5f && r >= 1 && r <= W - 3 && cc >= 1 && cc <= W - 3) {
+    const float h = dil[i];
+    const float dzdx = __fsub_rn(dil[i + 1], h), dzdy = __fsub_rn(dil[i + W], h);
+    const float nx = __fdiv_rn(-dzdy, c.res_f), ny = __fdiv_rn(-dzdx, c.res_f);
+    const float nn = __fsqrt_rn(__fadd_rn(__fmaf_rn(nx, nx, __fmul_rn(ny, ny)), 1.0f));
+    n0 = __fdiv_rn(nx, nn); n1 = __fdiv_rn(ny, nn); n2 = __fdiv_rn(1.0f, nn);
+  }
+  normal[i] = n0; normal[c.C + i] = n1; normal[2 * c.C + i] = n2;
+}
+
+// ------------------------------------------------------------------------------------------
+// pose / time
+// EM.py:200-226: roll by (sx, sy) cells, pad the vacated strips (0, variance = initial), add dz to
+// elevation and upper_bound (float32 plane + float64 scalar -> computed in double, stored fp32).
+__global__ void __launch_bounds__(256)
+k_shift(const DevCfg c, const float* __restrict__ src, float* __restrict__ dst, int sx, int sy, double dz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int layer = blockIdx.y;
+  if (i >= c.C) return;
+  const int W = c.W, r = i / W, cc = i - r * W;
+  const bool pad = (sx > 0 && r < sx) || (sx < 0 && r >= W + sx) || (sy > 0 && cc < sy) || (sy < 0 && cc >= W + sy);
+  float v;
+  if (pad) v = (layer == L_V) ? c.init_var : 0.f;
+  else {
+    int rs = r - sx, cs = cc - sy;
+    rs = ((rs % W) + W) % W; cs = ((cs % W) + W) % W;
+    v = src[(size_t)layer * c.C + rs * W + cs];
+  }
+  if (layer == L_H || layer == L_UPPER) v = (float)((double)v + dz);
+  dst[(size_t)layer * c.C + i] = v;
+}
+__global__ void __launch_bounds__(256) k_shift_z(const DevCfg c, float* __restrict__ map, double dz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.C) return;
+  map[i] = (float)((double)map[i] + dz);
+  map[5 * c.C + i] = (float)((double)map[5 * c.C + i] + dz);
+}
+__global__ void __launch_bounds__(256) k_clear(const DevCfg c, float* __restrict__ map) {   // EM.py:119-125
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.C) return;
+  for (int l = 0; l < 7; l++) map[(size_t)l * c.C + i] = (l == L_V) ? c.init_var : 0.f;
+}
+__global__ void __launch_bounds__(256) k_init(const DevCfg c, float* __restrict__ map) {    // EM.py:68-85
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.C) return;
+  for (int l = 0; l < 7; l++) map[(size_t)l * c.C + i] = (l == L_V) ? c.init_var : (l == L_TRAV ? 1.f : 0.f);
+}
+__global__ void __launch_bounds__(256) k_update_variance(const DevCfg c, float* __restrict__ map) {   // EM.py:420-422
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.C) return;
+  map[c.C + i] = __fadd_rn(map[c.C + i], __fmul_rn(c.time_var_f, map[2 * c.C + i]));
+}
+__global__ void __launch_bounds__(256) k_update_time(const DevCfg c, float* __restrict__ map) {       // EM.py:424-426
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.C) return;
+  map[4 * c.C + i] = __fadd_rn(map[4 * c.C + i], c.time_int_f);
+}
+
+// ------------------------------------------------------------------------------------------
+// export EM.py:579-670,720-775: NaN-fill, +center_z, crop the border ring, flip both axes.
+// kind: 0 elevation, 1 variance, 2 traversability, 3 time, 4 upper_bound, 5 is_upper_bound, 6..8 normal xyz
+// kind 9: arbitrary plane with flags (bit0 fill_nan, bit1 add_z) = process_map_for_publish (EM.py:579-596)
+__global__ void __launch_bounds__(256)
+k_export(const DevCfg c, const float* __restrict__ map, const float* __restrict__ normal, float* __restrict__ out,
+         int kind, float center_z, int only_above, const float* __restrict__ plane, int flags) {
+  const int Wo = c.W - 2;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= Wo * Wo) return;
+  const int orow = o / Wo, ocol = o - orow * Wo;
+  const int r = Wo - 1 - orow + 1, cc = Wo - 1 - ocol + 1;         // flip(0), flip(1) of m[1:-1,1:-1]
+  const int i = r * c.W + cc, C = c.C;
+  const float nanv = __int_as_float(0x7fc00000);
+  const float valid = map[2 * C + i], isup = map[6 * C + i], upper = map[5 * C + i];
+  float v;
+  switch (kind) {
+    case 0: v = (valid > 0.5f) ? __fadd_rn(map[i], center_z) : nanv; break;
+    case 1: v = map[C + i]; break;
+    case 2: {   // EM.py:615-628: NaN where neither valid nor upper-bounded; only [3:-3] is ever defined
+      const bool in33 = r >= 3 && r <= c.W - 4 && cc >= 3 && cc <= c.W - 4;
+      v = (in33 && __fadd_rn(valid, isup) > 0.5f) ? map[3 * C + i] : nanv; break; }
+    case 3: v = map[4 * C + i]; break;
+    case 4: case 5: {
+      const bool ok = only_above ? ((upper > 0.f && isup > 0.5f) || valid > 0.5f) : (valid > 0.5f || isup > 0.5f);
+      v = ok ? (kind == 4 ? __fadd_rn(upper, center_z) : isup) : nanv; break; }
+    case 9: {
+      v = plane[i];
+      if ((flags & 1) && !(valid > 0.5f)) v = nanv;
+      if (flags & 2) v = __fadd_rn(v, center_z);
+      break; }
+    default: v = normal[(size_t)(kind - 6) * C + i]; break;
+  }
+  out[o] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// plugins
+// plugins/min_filter.py:57-82 with Jacobi order (reads iteration k-1, writes iteration k).
+// `unfilled[it]` counts cells whose mask is still <= 0.5 after iteration it; an iteration whose
+// predecessor left none is skipped on the device (min_filter.py:115 breaks on the host instead).
+__global__ void __launch_bounds__(256)
+k_min_filter_iter(const DevCfg c, int k, const float* __restrict__ mask0, const float* __restrict__ in_h,
+                  const float* __restrict__ in_m, float* __restrict__ out_h, float* __restrict__ out_m,
+                  int* __restrict__ unfilled, int it) {
+  if (it > 0 && unfilled[it - 1] == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) unfilled[it] = 0; return; }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int miss = 0;
+  if (i < c.C) {
+    const int W = c.W;
+    float h = in_h[i], m = in_m[i];
+    if (mask0[i] < 0.5f) {
+      float mv = 1000000.0f;
+      for (int dy = -k; dy <= k; dy++)
+        for (int dx = -k; dx <= k; dx++) {
+          const int idx = i + W * dy + dx;
+          if (idx < 0 || idx >= c.C) continue;
+          const int ix = idx / W, iy = idx - ix * W;
+          if (ix <= 0 || ix >= W - 1 || iy <= 0 || iy >= W - 1) continue;
+          const float val = in_h[idx];
+          if (in_m[idx] > 0.5f && val < mv) mv = val;
+        }
+      if (mv < 1000000.f - 1.f) { h = mv; m = 0.6f; }
+    }
+    out_h[i] = h; out_m[i] = m;
+    miss = !(m > 0.5f);
+  }
+  miss = __syncthreads_count(miss);
+  if (threadIdx.x == 0 && miss) atomicAdd(unfilled + it, miss);
+}
+// final select: the result is in buffer parity (first it with unfilled[it]==0, else iteration_n-1)
+__global__ void __launch_bounds__(256)
+k_min_filter_final(const DevCfg c, const float* __restrict__ hA, const float* __restrict__ mA,
+                   const float* __restrict__ hB, const float* __restrict__ mB, const int* __restrict__ unfilled,
+                   int iteration_n, float* __restrict__ out, int* __restrict__ iters_run) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int last = iteration_n - 1;
+  for (int it = 0; it < iteration_n; it++) if (unfilled[it] == 0) { last = it; break; }
+  if (i == 0 && iters_run) *iters_run = last + 1;
+  if (i >= c.C) return;
+  // iteration `it` wrote buffer (it & 1) ? A : B   (it 0 reads A(copy of input) -> writes B)
+  const float* h = (last & 1) ? hA : hB; const float* m = (last & 1) ? mA : mB;
+  out[i] = m[i] > 0.5f ? h[i] : __int_as_float(0x7fc00000);
+}
+
+// plugins/smooth_filter.py:57-58: one 1-D pass of a size-3 uniform filter, 'reflect' boundary,
+// double accumulation of x*(1/3) terms, fp32 store (cupyx.scipy.ndimage correlate1d).
+__global__ void __launch_bounds__(256)
+k_box3(const DevCfg c, const float* __restrict__ in, float* __restrict__ out, int axis) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.C) return;
+  const int W = c.W, r = i / W, cc = i - r * W;
+  const double w = 1.0 / 3.0;
+  int ia, ib;
+  if (axis == 0) { ia = (r == 0 ? 0 : r - 1) * W + cc; ib = (r == W - 1 ? W - 1 : r + 1) * W + cc; }
+  else { ia = r * W + (cc == 0 ? 0 : cc - 1); ib = r * W + (cc == W - 1 ? W - 1 : cc + 1); }
+  const double sacc = __dadd_rn(__dadd_rn(__dmul_rn((double)in[ia], w), __dmul_rn((double)in[i], w)), __dmul_rn((double)in[ib], w));
+  out[i] = (float)sacc;
+}

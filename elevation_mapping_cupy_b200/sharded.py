@@ -1,0 +1,122 @@
+"""Many-sensor frames sharded across GPUs: one process per GPU, replicated grid,
+each rank fuses its own sensors' clouds, and the per-cell partial results are all-reduced over
+NCCL / NVLink between the phases of the frame:
+
+    begin (index + error count)  -> exchange 1: counts (int32 SUM), drift statistics (int64 SUM)
+    phase 1 (drift, Kalman)      -> exchange 2: sum new_h / new_v (int64 SUM, 2^-32 fixed point), counts
+                                                (int32 SUM), last-writer keys (int64 MAX)
+    phase 2 (ray-cast)           -> exchange 3: validity decrements (int64 SUM), counts (int32 SUM),
+                                                upper-bound keys (int32 MIN)
+    phase 3 (finalise + dilation + traversability + normals), identical on every rank.
+
+Every reduction is over integers, so the replicas stay bit-identical and the result equals the
+single-GPU `input_sensors` of the concatenated clouds bit for bit (which tests/ check against the oracle).
+The reference has no multi-GPU path; sensors there are fused sequentially.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+# emap_exchange.kind -> (torch dtype name, reduce op name)
+KIND = {0: ("int64", "SUM"), 1: ("int64", "MAX"), 2: ("int32", "MIN"), 3: ("int32", "SUM")}
+_TYPESTR = {"int64": "<i8", "int32": "<i4"}
+
+
+class _Buf:
+    def __init__(self, ptr, count, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+        self._owner = owner
+
+
+def reduce_plan(exchanges):
+    """[(ptr, count, kind)] -> [(ptr, count, dtype_name, op_name)] (pure host logic, unit-tested on CPU)."""
+    return [(p, n, *KIND[k]) for (p, n, k) in exchanges]
+
+
+def all_reduce_buffers(tensors_and_ops, group=None):
+    """In-place all-reduce of each (tensor, op_name); works for NCCL (CUDA tensors) and gloo (CPU)."""
+    import torch.distributed as dist
+    ops = {"SUM": dist.ReduceOp.SUM, "MAX": dist.ReduceOp.MAX, "MIN": dist.ReduceOp.MIN}
+    for t, op in tensors_and_ops:
+        dist.all_reduce(t, op=ops[op], group=group)
+
+
+def global_point_offsets(local_count, group=None):
+    """Rank-ordered exclusive prefix of the per-rank point counts: (my_offset, total)."""
+    import torch
+    import torch.distributed as dist
+    ws, rk = dist.get_world_size(group), dist.get_rank(group)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    mine = torch.tensor([int(local_count)], dtype=torch.int64, device=dev)
+    allc = [torch.zeros_like(mine) for _ in range(ws)]
+    dist.all_gather(allc, mine, group=group)
+    counts = [int(c.item()) for c in allc]
+    return sum(counts[:rk]), sum(counts)
+
+
+class ShardedElevationMap:
+    """Wraps one ElevationMap replica per rank; `input_sensors` is collective over `group`."""
+
+    def __init__(self, elevation_map, group=None, static_offsets=None):
+        import torch
+        self.em = elevation_map
+        self.group = group
+        self.torch = torch
+        self.static_offsets = static_offsets      # (my_offset, total) when every rank's count is fixed
+        em = self.em
+        # run the library on torch's current stream so kernels and NCCL collectives are stream-ordered
+        em._check(em._L.emap_set_stream(em._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self._cache = {}
+
+    def _exchange(self, phase):
+        em = self.em
+        arr = (_lib.EmapExchange * 4)()
+        n = C.c_int32(4)
+        em._check(em._L.emap_shard_exchange(em._h, phase, arr, C.byref(n)))
+        plan = reduce_plan([(arr[i].ptr, arr[i].count, arr[i].kind) for i in range(n.value)])
+        todo = []
+        for ptr, count, dt, op in plan:
+            key = (ptr, count, dt)
+            t = self._cache.get(key)
+            if t is None:
+                t = self.torch.as_tensor(_Buf(ptr, count, _TYPESTR[dt], em), device=f"cuda:{em.device}")
+                self._cache[key] = t
+            todo.append((t, op))
+        all_reduce_buffers(todo, self.group)
+
+    def input_sensors(self, clouds, Rs, ts, position_noise, orientation_noise, device_ptrs=False, overlap_z=None):
+        """`overlap_z`: absolute z of the frame's first sensor (rank 0's), the same value on every rank."""
+        em = self.em
+        ns = len(clouds)
+        keep, ptrs, counts = [], (C.c_void_p * ns)(), (C.c_int64 * ns)()
+        stride = dt = None
+        from .elevation_mapping import _device_pointer, _to_host
+        for i, c in enumerate(clouds):
+            dev = _device_pointer(c) if device_ptrs else None
+            if dev is not None:
+                ptr, n, row, d, k = dev
+            else:
+                a = np.ascontiguousarray(_to_host(c))
+                if a.dtype not in (np.float32, np.float64):
+                    a = a.astype(np.float32)
+                ptr, n, row, d, k = a.ctypes.data, a.shape[0], a.shape[1], (_lib.EMAP_F32 if a.dtype == np.float32 else _lib.EMAP_F64), a
+            stride, dt = (row, d) if stride is None else (stride, dt)
+            keep.append(k); ptrs[i] = ptr; counts[i] = n
+        total_local = sum(int(c) for c in counts)
+        off, _total = self.static_offsets if self.static_offsets else global_point_offsets(total_local, self.group)
+        Rm = np.ascontiguousarray(np.stack([np.asarray(_to_host(r), np.float32).reshape(9) for r in Rs]))
+        tm = np.ascontiguousarray(np.stack([np.asarray(_to_host(t), np.float32).reshape(3) for t in ts]))
+        L, h = em._L, em._h
+        em._check(L.emap_shard_begin(h, ns, ptrs, counts, stride, dt, int(bool(device_ptrs)), Rm.ctypes.data,
+                                     tm.ctypes.data, off, float(position_noise), float(orientation_noise)))
+        if overlap_z is not None:
+            em._check(L.emap_shard_set_overlap_z(h, float(overlap_z)))
+        self._exchange(1)
+        em._check(L.emap_shard_phase(h, 1))
+        self._exchange(2)
+        em._check(L.emap_shard_phase(h, 2))
+        self._exchange(3)
+        em._check(L.emap_shard_phase(h, 3))

@@ -250,7 +250,7 @@ void oracle_normal(int W, double resolution, const float* map, const float* mask
 /* TF.py:15-42: three dilated 3x3 convs (1->4 ch, dilation 1/2/3, valid), crop
  * to the common (W-6)^2, |.|, 1x1 conv over the 12 channels, exp(-x).
  * Summation order: taps row-major within a channel, channels in order.
- * out is (W-6)*(W-6).  fp32 throughout (plain multiply-add, no contraction). */
+ * out is (W-6)*(W-6).  fp32 fused multiply-adds in that order (cuDNN's own order is unspecified). */
 void oracle_traversability(int W, const float* in, const float* w1, const float* w2, const float* w3,
                            const float* wout, float* out) {
     int Wo = W - 6;
@@ -265,8 +265,8 @@ void oracle_traversability(int W, const float* in, const float* w1, const float*
                     float s = 0.f;
                     for (int a = 0; a < 3; a++)
                         for (int b = 0; b < 3; b++)
-                            s += ws[l][ch * 9 + a * 3 + b] * in[(cr + (a - 1) * dil) * W + (cc + (b - 1) * dil)];
-                    acc += wout[l * 4 + ch] * fabsf(s);
+                            s = fmaf(ws[l][ch * 9 + a * 3 + b], in[(cr + (a - 1) * dil) * W + (cc + (b - 1) * dil)], s);
+                    acc = fmaf(wout[l * 4 + ch], fabsf(s), acc);
                 }
             }
             out[r * Wo + c] = expf(-acc);

@@ -1,0 +1,128 @@
+"""GPU parity: the CUDA engine (through the C ABI / ElevationMap) against the CPU oracle on the same
+seeded inputs.  Bar: bit-identical cell indices; height / variance (and every other state plane) bit-identical
+to the canonical-serialisation oracle, which is stricter than the 1e-4 of BASELINE.json; traversability 2e-6."""
+import numpy as np
+import pytest
+
+from helpers import compare_state
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(param):
+    from elevation_mapping_cupy_b200.elevation_mapping import ElevationMap
+    return ElevationMap(param)
+
+
+def test_point_index_bit_exact_reference_test_shape(oracle_mod):
+    """Reference test workload (test_elevation_mapping.py:51-61): rand(100000,3) cloud, rand(3,3) R, rand(3) t."""
+    from elevation_mapping_cupy_b200.parameter import Parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = Parameter(); p.update()
+    em = _mk(p)
+    for seed in range(3):
+        pts, R, t = wl.reference_test_cloud(seed)
+        pts = (pts * np.float32(8.0) - np.float32(4.0)).astype(np.float32) if seed else pts
+        em.input_pointcloud(pts, ["x", "y", "z"], R, t, 0, 0)
+        idx, valid, inside = em.get_point_record(len(pts))
+        t_rel = (t - em.center).astype(np.float32)
+        oi, ov, oin, _ = oracle_mod.point_index(p, pts, R, t_rel)
+        assert np.array_equal(idx, oi)
+        assert np.array_equal(valid, ov)
+        assert np.array_equal(inside, oin)
+
+
+@pytest.mark.parametrize("cell_n,frames", [(256, 6), (202, 4)])
+def test_frames_match_oracle(oracle_mod, cell_n, frames):
+    """Config A style: several frames with move_to / update_variance / update_time in between."""
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = core_parameter(cell_n)
+    em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+    for f in range(frames):
+        if f % 2 == 0:
+            pts, R, t = wl.uniform_cloud(0, f, n=10000, half_extent=min(4.9, 0.02 * cell_n - 0.3))
+        else:
+            pts, R, t = wl.lidar_cloud(0, f, n_rings=32, n_az=625, max_range=8.0)
+        for m in (em, om):
+            m.move_to(t, R)
+            m.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+        state, normal = em.get_state()
+        compare_state(state, normal, om, label=f"frame {f}")
+        st = em.get_frame_stats()
+        assert st.error_cnt == om.stats.error_cnt
+        assert st.drift_applied == om.stats.drift_applied
+        assert np.float32(st.mean_error) == np.float32(om.mean_error) or not om.stats.drift_evaluated
+        for m in (em, om):
+            m.update_variance(); m.update_time()
+        state, normal = em.get_state()
+        compare_state(state, normal, om, label=f"frame {f} after ticks")
+
+
+def test_nan_rows_and_f64_input(oracle_mod):
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = core_parameter(256)
+    em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+    pts, R, t = wl.uniform_cloud(0, 3, n=5000)
+    pts[::7] = np.nan
+    pts64 = np.concatenate([pts.astype(np.float64), np.zeros((len(pts), 2))], 1)   # extra channels, float64 rows
+    em.input_pointcloud(pts64, ["x", "y", "z", "a", "b"], R, t, 0.0, 0.0)
+    om.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.0, 0.0)
+    state, normal = em.get_state()
+    compare_state(state, normal, om, label="nan/f64")
+    idx, valid, inside = em.get_point_record(len(pts))
+    assert (idx[::7] == -1).all() and (valid[::7] == 0).all()
+
+
+def test_export_layers_match_oracle(oracle_mod):
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    for only_above in (False, True):
+        p = core_parameter(202, use_only_above_for_upper_bound=only_above)
+        em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+        for f in range(3):
+            pts, R, t = wl.lidar_cloud(0, f, n_rings=32, n_az=625, max_range=8.0)
+            for m in (em, om):
+                m.move_to(t + np.float32(0.3), R)
+                m.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+        data = np.zeros((p.cell_n - 2, p.cell_n - 2), np.float32)
+        for name in ["elevation", "variance", "traversability", "time", "upper_bound", "is_upper_bound",
+                     "normal_x", "normal_y", "normal_z"]:
+            em.get_map_with_name_ref(name, data)
+            ref = om.export_layer(name)
+            tol = 2e-6 if name == "traversability" else 0.0
+            assert np.array_equal(np.isnan(data), np.isnan(ref)), name
+            assert np.nanmax(np.abs(data - ref), initial=0.0) <= tol, name
+
+
+def test_multi_sensor_frame_matches_oracle(oracle_mod):
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = core_parameter(256)
+    em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+    for f in range(3):
+        clouds, Rs, ts = [], [], []
+        for s in range(3):
+            pts, R, t = wl.lidar_cloud(2, f, n_rings=16, n_az=500, max_range=6.0, sensor=s, n_sensors=3)
+            clouds.append(pts); Rs.append(R); ts.append(t)
+        em.input_sensors(clouds, Rs, ts, 0.02, 0.02)
+        om.input_sensors(clouds, Rs, ts, 0.02, 0.02)
+        state, normal = em.get_state()
+        compare_state(state, normal, om, label=f"multi-sensor frame {f}")
+
+
+def test_config_b_single_frame(oracle_mod):
+    """BASELINE config B at full size: 1024^2, 200k-point LiDAR frame, raycast + overlap clear on."""
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = core_parameter(1024)
+    em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+    for f in range(2):
+        pts, R, t = wl.lidar_cloud(1, f)
+        for m in (em, om):
+            m.move_to(t, R)
+            m.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+            m.update_time()
+    state, normal = em.get_state()
+    compare_state(state, normal, om, label="config B")
