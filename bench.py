@@ -179,6 +179,8 @@ def main():
     if args.gpus > 1 and world != args.gpus:
         raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local_rank)
+    # one explicit stream for everything (library kernels, torch memsets, NCCL ordering, timing events)
+    torch.cuda.set_stream(torch.cuda.Stream())
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -201,9 +203,10 @@ def main():
     dev_pts = [torch.from_numpy(p).cuda() for p, _, _ in frames]
     pin_pts = [torch.from_numpy(p).pin_memory() for p, _, _ in frames]
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.current_stream()      # the side stream made current below
+    assert stream.cuda_stream != 0
     if sh is None:
-        em._check(em._L.emap_set_stream(em._h, torch.cuda.current_stream().cuda_stream))
+        em._check(em._L.emap_set_stream(em._h, stream.cuda_stream))
 
     def between(f):
         R0, t0 = poses0[f]

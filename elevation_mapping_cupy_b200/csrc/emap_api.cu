@@ -210,11 +210,8 @@ int frame_begin(emap_handle* h, int32_t n_sensors, const void* const* points, co
     make_pose(R + 9 * s, tr, &h->poses[s]);
   }
   // frame scalars: keep mean / additive error, zero the accumulators
-  CK(cudaMemsetAsync(h->fs, 0, offsetof(FrameScalars, shift), h->stream));
-  {
-    float tz = h->poses[0].t[2];
-    CK(cudaMemcpyAsync(&h->fs->overlap_tz, &tz, sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  }
+  k_frame_reset<<<1, 32, 0, h->stream>>>(h->fs, h->poses[0].t[2], 1);
+  LAUNCH_CHECK();
   if (stage_mark(h, 0)) return EMAP_ERR_CUDA;
   const void* dev_pts[64];
   std::vector<const void*> dev_vec;
@@ -272,12 +269,13 @@ int frame_rays(emap_handle* h) {
     k_record<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs);
     LAUNCH_CHECK();
     if (stage_mark(h, 4)) return EMAP_ERR_CUDA;
-    const size_t sm = sizeof(float) * (size_t)h->dc.n_steps;
+    const size_t sm = sizeof(float) * (size_t)((h->dc.n_steps + 31) & ~31);
     for (size_t s = 0; s + 1 < h->offs.size(); s++) {
       const i64 n = h->offs[s + 1] - h->offs[s];
-      if (n <= 0) continue;
-      k_raycast<<<cdiv(n, 128), 128, sm, h->stream>>>(h->dc, h->poses[s], n, h->xyzv + h->offs[s], h->pidx + h->offs[s],
-                                                       h->normal, h->sc, h->steps, h->fs, h->count_rays);
+      if (n <= 0 || h->dc.n_steps == 0) continue;
+      k_raycast<<<cdiv(n, RC_PTS), RC_PTS, sm, h->stream>>>(h->dc, h->poses[s], n, h->xyzv + h->offs[s],
+                                                             h->pidx + h->offs[s], h->map, h->normal, h->sc, h->steps,
+                                                             h->fs, h->count_rays);
       LAUNCH_CHECK();
     }
   } else if (stage_mark(h, 4)) return EMAP_ERR_CUDA;
@@ -293,7 +291,13 @@ size_t post_smem(const DevCfg& d) {
 
 int launch_post(emap_handle* h) {
   dim3 grid(cdiv(h->dc.W, PT_X), cdiv(h->dc.W, PT_Y));
-  k_post<<<grid, 256, post_smem(h->dc), h->stream>>>(h->dc, h->map, h->trav_input, h->normal);
+  const size_t sm = post_smem(h->dc);
+  switch (h->dc.dilation) {
+    case 1: k_post<1><<<grid, 256, sm, h->stream>>>(h->dc, h->map, h->trav_input, h->normal); break;
+    case 2: k_post<2><<<grid, 256, sm, h->stream>>>(h->dc, h->map, h->trav_input, h->normal); break;
+    case 3: k_post<3><<<grid, 256, sm, h->stream>>>(h->dc, h->map, h->trav_input, h->normal); break;
+    default: k_post<0><<<grid, 256, sm, h->stream>>>(h->dc, h->map, h->trav_input, h->normal); break;
+  }
   LAUNCH_CHECK();
   return 0;
 }
@@ -321,13 +325,19 @@ int alloc_plugin_scratch(emap_handle* h) {
   return 0;
 }
 
-__global__ void k_ukey_extract(int C, const uint4* __restrict__ rec, int* __restrict__ x) {
+// upper-bound keys of a sharded frame: invalid cells carry theirs in rec.x, valid cells in ukv
+__global__ void k_ukey_extract(int C, const uint2* __restrict__ rec, const u32* __restrict__ ukv, int* __restrict__ x) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < C) x[i] = (int)(rec[i].z ^ 0x80000000u);      // order-preserving u32 -> s32
+  if (i >= C) return;
+  const uint2 r = rec[i];
+  const u32 k = (r.y & RF_VALID) ? ukv[i] : r.x;
+  x[i] = (int)(k ^ 0x80000000u);                         // order-preserving u32 -> s32
 }
-__global__ void k_ukey_merge(int C, uint4* __restrict__ rec, const int* __restrict__ x) {
+__global__ void k_ukey_merge(int C, uint2* __restrict__ rec, u32* __restrict__ ukv, const int* __restrict__ x) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < C) rec[i].z = ((u32)x[i]) ^ 0x80000000u;
+  if (i >= C) return;
+  const u32 k = ((u32)x[i]) ^ 0x80000000u;
+  if (rec[i].y & RF_VALID) ukv[i] = k; else rec[i].x = k;
 }
 
 }  // namespace
@@ -377,10 +387,11 @@ int emap_create(const emap_config* cfg, int device, emap_handle** out) {
   ALLOC(h->u32_block, sizeof(u32) * 5 * C);
   ALLOC(h->i64_block, sizeof(i64) * 3 * C);
   ALLOC(h->sc.last, sizeof(u64) * C);
-  ALLOC(h->sc.rec, sizeof(uint4) * C);
+  ALLOC(h->sc.rec, sizeof(uint2) * C);
+  ALLOC(h->sc.ukv, sizeof(u32) * C);
   ALLOC(h->ukey_x, sizeof(int) * C);
   ALLOC(h->fs, sizeof(FrameScalars));
-  ALLOC(h->steps, sizeof(float) * (h->steps_host.size() + 1));
+  ALLOC(h->steps, sizeof(float) * (h->steps_host.size() + 32));
   ALLOC(h->d_export, sizeof(float) * C);
 #undef ALLOC
   h->sc.cnt_all = h->u32_block; h->sc.cnt_inl = h->u32_block + C; h->sc.cnt_fused = h->u32_block + 2 * C;
@@ -389,18 +400,22 @@ int emap_create(const emap_config* cfg, int device, emap_handle** out) {
   cudaMemsetAsync(h->u32_block, 0, sizeof(u32) * 5 * C, h->stream);
   cudaMemsetAsync(h->i64_block, 0, sizeof(i64) * 3 * C, h->stream);
   cudaMemsetAsync(h->sc.last, 0, sizeof(u64) * C, h->stream);
-  cudaMemsetAsync(h->sc.rec, 0, sizeof(uint4) * C, h->stream);
+  cudaMemsetAsync(h->sc.rec, 0, sizeof(uint2) * C, h->stream);
+  cudaMemsetAsync(h->sc.ukv, 0xff, sizeof(u32) * C, h->stream);      // UKEY_NONE
   cudaMemsetAsync(h->normal, 0, sizeof(float) * 3 * C, h->stream);
   cudaMemsetAsync(h->trav_input, 0, sizeof(float) * C, h->stream);
   cudaMemsetAsync(h->fs, 0, sizeof(FrameScalars), h->stream);
-  if (!h->steps_host.empty())
-    cudaMemcpyAsync(h->steps, h->steps_host.data(), sizeof(float) * h->steps_host.size(), cudaMemcpyHostToDevice, h->stream);
+  {   // pad the march table to a multiple of 32 with +inf (k_raycast reads whole warps of steps)
+    std::vector<float> padded(h->steps_host);
+    while (padded.size() % 32 || padded.empty()) padded.push_back(INFINITY);
+    cudaMemcpy(h->steps, padded.data(), sizeof(float) * padded.size(), cudaMemcpyHostToDevice);
+  }
   k_init<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map);
   h->launches++;
   if (post_smem(h->dc) > 48 * 1024)
-    cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(h->dc));
-  if (sizeof(float) * h->steps_host.size() > 48 * 1024)
-    cudaFuncSetAttribute(k_raycast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * h->steps_host.size()));
+    cudaFuncSetAttribute(k_post<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(h->dc));
+  if (sizeof(float) * (h->steps_host.size() + 32) > 40 * 1024)
+    cudaFuncSetAttribute(k_raycast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (h->steps_host.size() + 32)));
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail("init", e);
   if ((e = cudaGetLastError()) != cudaSuccess) return bail("init", e);
   *out = h;
@@ -413,7 +428,7 @@ int emap_destroy(emap_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   void* ptrs[] = {h->map, h->map_alt, h->normal, h->trav_input, h->u32_block, h->i64_block, h->sc.last, h->sc.rec,
-                  h->ukey_x, h->fs, h->steps, h->d_export, h->d_in[0], h->d_in[1], h->xyzv, h->pidx, h->pl[0], h->pl[1],
+                  h->sc.ukv, h->ukey_x, h->fs, h->steps, h->d_export, h->d_in[0], h->d_in[1], h->xyzv, h->pidx, h->pl[0], h->pl[1],
                   h->pl[2], h->pl[3], h->pl_cnt};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int b = 0; b < 2; b++) if (h->in_free[b]) cudaEventDestroy(h->in_free[b]);
@@ -472,9 +487,8 @@ int emap_shard_begin(emap_handle* h, int32_t n_sensors, const void* const* point
 int emap_shard_set_overlap_z(emap_handle* h, float z_abs) {
   ENTER(h);
   if (h->phase < 1) return fail(h, EMAP_ERR_STATE, "emap_shard_set_overlap_z must follow emap_shard_begin");
-  const float tz = z_abs - h->center[2];
-  CK(cudaMemcpyAsync(&h->fs->overlap_tz, &tz, sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  k_frame_reset<<<1, 32, 0, h->stream>>>(h->fs, z_abs - h->center[2], 0);
+  LAUNCH_CHECK();
   return EMAP_OK;
 }
 
@@ -496,7 +510,7 @@ int emap_shard_exchange(emap_handle* h, int32_t phase, emap_exchange* out, int32
   } else if (phase == 3) {   // after the ray-cast: decrements, counts, upper-bound keys
     if (h->phase != 3) return fail(h, EMAP_ERR_STATE, "exchange 3 must follow phase 2");
     if (h->dc.visibility) {
-      k_ukey_extract<<<cdiv(C, 256), 256, 0, h->stream>>>((int)C, h->sc.rec, h->ukey_x);
+      k_ukey_extract<<<cdiv(C, 256), 256, 0, h->stream>>>((int)C, h->sc.rec, h->sc.ukv, h->ukey_x);
       LAUNCH_CHECK();
       out[0] = {h->sc.DV, C, 0};
       out[1] = {h->sc.n_ray, C, 3};
@@ -521,7 +535,7 @@ int emap_shard_phase(emap_handle* h, int32_t phase) {
   if (phase == 3) {
     if (h->phase != 3 && h->phase != 4) return fail(h, EMAP_ERR_STATE, "phase 3 must follow phase 2");
     if (h->phase == 4) {
-      k_ukey_merge<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc.C, h->sc.rec, h->ukey_x);
+      k_ukey_merge<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc.C, h->sc.rec, h->sc.ukv, h->ukey_x);
       LAUNCH_CHECK();
     }
     return frame_finish(h);

@@ -28,7 +28,8 @@ struct CellScratch {
   i64* SV;         // sum new_v   CK.py:184
   i64* DV;         // sum of validity decrements CK.py:250
   u64* last;       // (global point index << 32 | bits(new_h)) max  -> upper_bound of a hit cell, CK.py:191
-  uint4* rec;      // ray record {h', v', ukey, flags}
+  uint2* rec;      // ray record, 8 B: {valid cell ? bits(h') : upper-bound key, flags}
+  u32* ukv;        // upper-bound key carved into VALID cells by penetrating rays (UKEY_NONE between frames)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -81,6 +82,13 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
     if (ec) atomicAdd((u64*)&fs->ecnt, (u64)ec);
     if (nv) atomicAdd((u64*)&fs->nvalid, (u64)nv);
   }
+}
+
+// start of a frame: zero the accumulators (keep mean / additive error), set the overlap-clear reference
+__global__ void k_frame_reset(FrameScalars* fs, float overlap_tz, int zero) {
+  if (threadIdx.x || blockIdx.x) return;
+  if (zero) { fs->E = 0; fs->ecnt = 0; fs->nvalid = 0; fs->ray_steps = 0; fs->ray_visits = 0; }
+  fs->overlap_tz = overlap_tz;
 }
 
 // EM.py:346-357
@@ -136,85 +144,128 @@ __device__ __forceinline__ float add_n_times(float v, float c, u32 n) {
   return v;
 }
 
-// post-fusion state of a cell as a ray sees it (SURVEY 8(c) step 3 -> 4), packed to 16 B
+// post-fusion state of a cell as a ray sees it (SURVEY 8(c) step 3 -> 4), packed to 8 B:
+//   .x = bits(h' = h (+ drift shift))            for cells that are valid after the fusion stores
+//      = upper-bound key (UKEY_NONE if unbounded) for invalid cells -- rays atomicMin it in place
+//   .y = RF_* flags
+// The variance a ray needs (CK.py:239) is rebuilt on the rare second level from map[1] and n_out.
 __global__ void __launch_bounds__(256)
 k_record(const DevCfg c, const float* __restrict__ map, const CellScratch s, const FrameScalars* __restrict__ fs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.C) return;
-  float h = map[i];
-  if (fs->applied) h = __fadd_rn(h, fs->shift);
-  float v = add_n_times(map[c.C + i], c.c_out, s.n_out[i]);
   float valid = map[2 * c.C + i], time = map[4 * c.C + i];
-  float upper = map[5 * c.C + i], isup = map[6 * c.C + i];
-  u32 ukey;
-  if (s.cnt_fused[i] > 0) { valid = 1.f; time = 0.f; ukey = UKEY_NONE; }   // CK.py:187-192
-  else ukey = (isup < 0.5f) ? UKEY_NONE : fkey(upper);
-  u32 fl = (valid < 0.5f ? 0u : RF_VALID) | (time < 0.5f ? RF_T05 : 0u) | ((double)time < 1.0 ? RF_T10 : 0u)
+  const bool hit = s.cnt_fused[i] > 0;
+  if (hit) { valid = 1.f; time = 0.f; }                                     // CK.py:187-192
+  u32 fl = (time < 0.5f ? RF_T05 : 0u) | (time < 1.0f ? RF_T10 : 0u)
          | ((double)(float)s.cnt_inl[i] > c.wall_thresh ? RF_WALL : 0u);
-  s.rec[i] = make_uint4(__float_as_uint(h), __float_as_uint(v), ukey, fl);
+  u32 a;
+  if (valid < 0.5f) {
+    const float isup = map[6 * c.C + i];
+    a = (hit || isup < 0.5f) ? UKEY_NONE : fkey(map[5 * c.C + i]);
+  } else {
+    fl |= RF_VALID;
+    float h = map[i];
+    if (fs->applied) h = __fadd_rn(h, fs->shift);
+    a = __float_as_uint(h);
+  }
+  s.rec[i] = make_uint2(a, fl);
 }
 
-// CK.py:198-259 ray-cast half: one thread per valid point.  `steps` is the shared table of the
-// fp16 march variable s_k (s_0 = half(step), s_{k+1} = half(float(double(s_k) + step)), CK.py:203).
-__global__ void __launch_bounds__(128)
+// CK.py:198-259 ray-cast half.  A CTA owns RC_PTS consecutive points: every thread sets up the ray of
+// one point (CK.py:83-101,199-201), the valid rays are compacted in shared memory, then each WARP
+// marches one ray at a time with its 32 lanes on 32 consecutive steps of the fp16 march variable
+// s_k (shared table: s_0 = half(step), s_{k+1} = half(float(double(s_k) + step)), CK.py:203).
+// "Same cell as the previous step" (CK.py:209-210) is a shuffle with the neighbouring lane.  The
+// effects of a visit are commutative integer atomics, so the lane order is irrelevant.
+#define RC_PTS 128
+__global__ void __launch_bounds__(RC_PTS)
 k_raycast(const DevCfg c, const Pose q, const i64 n, const float4* __restrict__ xyzv,
-          const int* __restrict__ pidx, const float* __restrict__ normal, const CellScratch s,
-          const float* __restrict__ steps, FrameScalars* fs, const int count) {
-  extern __shared__ float s_steps[];
-  for (int k = threadIdx.x; k < c.n_steps; k += blockDim.x) s_steps[k] = steps[k];
-  __syncthreads();
-  const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int prec = pidx[i];
-  if ((prec & (PT_VALID | PT_SKIP)) != PT_VALID) return;          // CK.py:226: invalid points do nothing
-  const float4 g = xyzv[i];
-  const float x = g.x, y = g.y, z = g.z;
-  // ray_vector CK.py:83-101
-  const float vx = h16(h16(x) - q.t16[0]), vy = h16(h16(y) - q.t16[1]), vz = h16(h16(z) - q.t16[2]);
-  const float norm = h16(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz))));
-  float rx = 0.f, ry = 0.f, rz = 0.f;
-  if (norm > 0.f) { rx = h16(__fdiv_rn(vx, norm)); ry = h16(__fdiv_rn(vy, norm)); rz = h16(__fdiv_rn(vz, norm)); }
-  const float len = fminf(norm, c.max_len16);                     // CK.py:201
-  const float dec = (float)(-c.cleanup_step / ((double)len / c.max_ray_length));   // CK.py:250
-  const i64 dec_fix = fix32(dec);
-  const int W = c.W;
-  int last_idx = -1;
-  int n_steps_done = 0, n_visits = 0;
-  for (int k = 0; k < c.n_steps; k++) {
-    const float sk = s_steps[k];
-    if (!(sk < len)) break;
-    n_steps_done++;
-    const float nx = __fmaf_rn(rx, sk, q.t[0]);                   // t + ray*s: product exact (CK.py:205-207)
-    const float ny = __fmaf_rn(ry, sk, q.t[1]);
-    const int ix = axis_cell(c, h16(nx)), iy = axis_cell(c, h16(ny));
-    const int nidx = ix * W + iy;
-    if (nidx == last_idx) continue;                               // CK.py:209
-    last_idx = nidx;
-    if (!cell_inside(W, ix, iy)) continue;                        // CK.py:211
-    const float nz = __fmaf_rn(rz, sk, q.t[2]);
-    const float ddx = x - nx, ddy = y - ny, ddz = z - nz;
-    float d = __fmul_rn(ddy, ddy); d = __fmaf_rn(ddx, ddx, d); d = __fmaf_rn(ddz, ddz, d);   // CK.py:225
-    d = h16(d);
-    if ((double)d < 0.1) continue;                                // CK.py:226
-    n_visits++;
-    const uint4 r = s.rec[nidx];
-    if (!(r.w & RF_VALID)) {                                      // CK.py:229-235 carve the upper bound
-      const u32 key = fkey(nz);
-      if (key < r.z) atomicMin(&s.rec[nidx].z, key);
-      continue;
+          const int* __restrict__ pidx, const float* __restrict__ map, const float* __restrict__ normal,
+          const CellScratch s, const float* __restrict__ steps, FrameScalars* fs, const int count) {
+  extern __shared__ float s_steps[];             // n_steps padded to a multiple of 32 with +inf
+  __shared__ float s_p[7][RC_PTS];
+  __shared__ i64 s_dec[RC_PTS];
+  __shared__ int s_wc[RC_PTS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_pad = (c.n_steps + 31) & ~31;
+  for (int k = tid; k < n_pad; k += RC_PTS) s_steps[k] = steps[k];
+  const i64 i = blockIdx.x * (i64)RC_PTS + tid;
+  bool ok = false;
+  float x = 0.f, y = 0.f, z = 0.f, rx = 0.f, ry = 0.f, rz = 0.f, len = 0.f;
+  i64 dec_fix = 0;
+  if (i < n) {
+    const int prec = pidx[i];
+    ok = (prec & (PT_VALID | PT_SKIP)) == PT_VALID;               // CK.py:226: invalid points do nothing
+    if (ok) {
+      const float4 g = xyzv[i];
+      x = g.x; y = g.y; z = g.z;
+      // ray_vector CK.py:83-101
+      const float vx = h16(h16(x) - q.t16[0]), vy = h16(h16(y) - q.t16[1]), vz = h16(h16(z) - q.t16[2]);
+      const float norm = h16(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz))));
+      if (norm > 0.f) { rx = h16(__fdiv_rn(vx, norm)); ry = h16(__fdiv_rn(vy, norm)); rz = h16(__fdiv_rn(vz, norm)); }
+      len = fminf(norm, c.max_len16);                             // CK.py:201
+      dec_fix = fix32((float)(-c.cleanup_step / ((double)len / c.max_ray_length)));   // CK.py:250
     }
-    if (r.w & RF_T05) continue;                                   // CK.py:237
-    const float nh = __uint_as_float(r.x), nv = __uint_as_float(r.y);
-    const double rhs = fma(-fmin((double)nv, 1.0), 0.05, (double)nz + 0.01);   // CK.py:239 (nvcc contraction)
-    if ((double)nh > rhs) {
-      const float n0 = h16(__ldg(normal + nidx)), n1 = h16(__ldg(normal + c.C + nidx)), n2 = h16(__ldg(normal + 2 * c.C + nidx));
+  }
+  const u32 bal = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) s_wc[warp] = __popc(bal);
+  __syncthreads();
+  int base = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < RC_PTS / 32; w++) { if (w < warp) base += s_wc[w]; total += s_wc[w]; }
+  if (ok) {
+    const int pos = base + __popc(bal & ((1u << lane) - 1u));
+    s_p[0][pos] = x; s_p[1][pos] = y; s_p[2][pos] = z; s_p[3][pos] = rx; s_p[4][pos] = ry; s_p[5][pos] = rz;
+    s_p[6][pos] = len; s_dec[pos] = dec_fix;
+  }
+  __syncthreads();
+  const int W = c.W, C = c.C;
+  const float tx = q.t[0], ty = q.t[1], tz = q.t[2];
+  int n_steps_done = 0, n_visits = 0;
+  for (int r = warp; r < total; r += RC_PTS / 32) {
+    x = s_p[0][r]; y = s_p[1][r]; z = s_p[2][r]; rx = s_p[3][r]; ry = s_p[4][r]; rz = s_p[5][r]; len = s_p[6][r];
+    dec_fix = s_dec[r];
+    int carry = -1;
+    for (int kb = 0; kb < n_pad; kb += 32) {
+      if (!(s_steps[kb] < len)) break;                            // warp-uniform
+      const float sk = s_steps[kb + lane];
+      const bool act = sk < len;
+      const float nx = __fmaf_rn(rx, sk, tx);                     // t + ray*s: product exact (CK.py:205-207)
+      const float ny = __fmaf_rn(ry, sk, ty);
+      const int ix = axis_cell(c, h16(nx)), iy = axis_cell(c, h16(ny));
+      const int nidx = act ? ix * W + iy : -2;
+      int prev = __shfl_up_sync(0xffffffffu, nidx, 1);
+      if (lane == 0) prev = carry;
+      carry = __shfl_sync(0xffffffffu, nidx, 31);
+      if (count) n_steps_done += act;
+      if (!act || nidx == prev) continue;                         // CK.py:209
+      if (!cell_inside(W, ix, iy)) continue;                      // CK.py:211
+      const float nz = __fmaf_rn(rz, sk, tz);
+      const float ddx = x - nx, ddy = y - ny, ddz = z - nz;
+      float d = __fmul_rn(ddy, ddy); d = __fmaf_rn(ddx, ddx, d); d = __fmaf_rn(ddz, ddz, d);   // CK.py:225
+      d = h16(d);
+      if (d < 0.1f) continue;      // CK.py:226 `d < 0.1` in double: no fp16 value lies in [0.1, 0.1f)
+      if (count) n_visits++;
+      const uint2 rc = s.rec[nidx];
+      if (!(rc.y & RF_VALID)) {                                   // CK.py:229-235 carve the upper bound
+        const u32 key = fkey(nz);
+        if (key < rc.x) atomicMin(&s.rec[nidx].x, key);
+        continue;
+      }
+      if (rc.y & RF_T05) continue;                                // CK.py:237
+      const float nh = __uint_as_float(rc.x);
+      // CK.py:239 needs nh > nz + 0.01 - min(v,1)*0.05 >= nz - 0.04: reject far-below cells in fp32
+      if (nh < nz - 0.05f) continue;
+      const float nv = add_n_times(__ldg(map + C + nidx), c.c_out, s.n_out[nidx]);
+      const double rhs = fma(-fmin((double)nv, 1.0), 0.05, (double)nz + 0.01);   // CK.py:239 (nvcc contraction)
+      if (!((double)nh > rhs)) continue;
+      const float n0 = h16(__ldg(normal + nidx)), n1 = h16(__ldg(normal + C + nidx)), n2 = h16(__ldg(normal + 2 * C + nidx));
       const float product = __fadd_rn(__fadd_rn(__fmul_rn(rx, n0), __fmul_rn(ry, n1)), __fmul_rn(rz, n2));   // CK.py:103-108
       if ((double)fabsf(product) < c.cos_thresh) continue;        // CK.py:245
-      if ((r.w & RF_WALL) && (r.w & RF_T10)) continue;            // CK.py:246-247
+      if ((rc.y & RF_WALL) && (rc.y & RF_T10)) continue;          // CK.py:246-247
       atomicAdd((u64*)(s.DV + nidx), (u64)dec_fix);               // CK.py:250
       atomicAdd(s.n_ray + nidx, 1u);                              // CK.py:251
-      const u32 key = fkey(nz);                                   // CK.py:253-256
-      if (key < r.z) atomicMin(&s.rec[nidx].z, key);
+      atomicMin(s.ukv + nidx, fkey(nz));                          // CK.py:253-256
     }
   }
   if (count) {
@@ -222,7 +273,7 @@ k_raycast(const DevCfg c, const Pose q, const i64 n, const float4* __restrict__ 
       n_steps_done += __shfl_down_sync(0xffffffffu, n_steps_done, o);
       n_visits += __shfl_down_sync(0xffffffffu, n_visits, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
       atomicAdd((u64*)&fs->ray_steps, (u64)n_steps_done);
       atomicAdd((u64*)&fs->ray_visits, (u64)n_visits);
     }
@@ -239,7 +290,6 @@ k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const F
   const int C = c.C;
   const u32 cf = s.cnt_fused[i], no = s.n_out[i], ca = s.cnt_all[i];
   const u32 nr = rays_ran ? s.n_ray[i] : 0u;
-  const u32 ukey = rays_ran ? s.rec[i].z : 0u;
   const int applied = fs->applied;
   const int r = i / c.W, col = i - r * c.W;
   const bool in_win = c.overlap && r >= c.cell_min && r < c.cell_max && col >= c.cell_min && col < c.cell_max;
@@ -253,12 +303,17 @@ k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const F
     upper = __uint_as_float((u32)(s.last[i] & 0xffffffffull));
   }
   if (rays_ran) {
+    const float valid_pf = valid;                                 // validity after the fusion stores
     const u32 key0 = (isup < 0.5f) ? UKEY_NONE : fkey(upper);
     if (nr > 0) {
       valid = __fadd_rn(valid, (float)unfix32(s.DV[i]));          // CK.py:250
       v = add_n_times(v, c.c_out, nr);                            // CK.py:251
     }
-    if (ukey != key0) { upper = funkey(ukey); isup = 1.f; }       // CK.py:230-233,253-256 (true min over rays)
+    // true min over rays (CK.py:230-233,253-256): invalid cells carry it in rec.x, valid cells in ukv
+    u32 ukey;
+    if (valid_pf < 0.5f) ukey = s.rec[i].x;
+    else { const u32 kv = s.ukv[i]; ukey = min(key0, kv); if (kv != UKEY_NONE) s.ukv[i] = UKEY_NONE; }
+    if (ukey != key0) { upper = funkey(ukey); isup = 1.f; }
   }
   // average_map_kernel CK.py:362-384
   const float valid_in = valid;
@@ -298,6 +353,7 @@ k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const F
 #define PT_Y 16
 
 // exact flat-index semantics of CK.py:403-418,429-438 for one cell, from global memory
+// (only used for the K-1 outermost columns on each side, where a window wraps into the adjacent row)
 __device__ float dilate_cell_global(const DevCfg& c, const float* __restrict__ up, const float* __restrict__ valid,
                                     const float* __restrict__ isup, int i) {
   const int W = c.W, k = c.dilation;
@@ -307,9 +363,9 @@ __device__ float dilate_cell_global(const DevCfg& c, const float* __restrict__ u
   for (int dy = -k; dy <= k; dy++)
     for (int dx = -k; dx <= k; dx++) {
       const int idx = i + W * dy + dx;
-      const int ix = idx / W, iy = idx % W;                        // C division, as the reference
-      if (ix <= 0 || ix >= W - 1 || iy <= 0 || iy >= W - 1) continue;
       if (idx < 0 || idx >= c.C) continue;
+      const int ix = idx / W, iy = idx % W;
+      if (ix <= 0 || ix >= W - 1 || iy <= 0 || iy >= W - 1) continue;
       if (__fadd_rn(valid[idx], isup[idx]) > 0.5f && (float)(dx + dy) < distance) {
         distance = (float)(dx + dy); near_value = up[idx];
       }
@@ -317,53 +373,64 @@ __device__ float dilate_cell_global(const DevCfg& c, const float* __restrict__ u
   return distance < 100.f ? near_value : h;
 }
 
+// K = dilation_size as a compile-time constant (0 = use c.dilation at run time).
+template <int KT>
 __global__ void __launch_bounds__(256)
 k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, float* __restrict__ normal) {
   extern __shared__ float smem[];
-  const int W = c.W, C = c.C, k = c.dilation;
-  const int HL = k + 3;                          // halo of the staged inputs
+  const int W = c.W, C = c.C;
+  const int K = KT ? KT : c.dilation;
+  const int HL = K + 3;                          // halo of the staged inputs
   const int A = PT_Y + 2 * HL, B = PT_X + 2 * HL;
-  const int DA = PT_Y + 6, DB = PT_X + 6;
-  float* s_up = smem;                            // A*B
-  float* s_mask = s_up + A * B;                  // A*B   is_valid + is_upper_bound
-  float* s_dil = s_mask + A * B;                 // DA*DB
+  constexpr int DA = PT_Y + 6, DB = PT_X + 6;
+  float* s_up = smem;                            // A*B   upper_bound
+  float* s_mask = s_up + A * B;                  // A*B   selectable neighbour: inside && is_valid + is_upper_bound > 0.5
+  float* s_dil = s_mask + A * B;                 // DA*DB dilated tile (+3 halo)
   const float* up = map + 5 * C; const float* valid = map + 2 * C; const float* isup = map + 6 * C;
   const int r0 = blockIdx.y * PT_Y, c0 = blockIdx.x * PT_X;
-  const int tid = threadIdx.x;
-  for (int e = tid; e < A * B; e += blockDim.x) {
-    const int a = e / B, b = e - a * B;
-    const int r = r0 - HL + a, cc = c0 - HL + b;
-    float u = 0.f, m = 0.f;
-    if (r >= 0 && r < W && cc >= 0 && cc < W) {
-      const int gi = r * W + cc;
-      u = __ldg(up + gi);
-      m = __fadd_rn(__ldg(valid + gi), __ldg(isup + gi));
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  // stage: s_mask holds the raw mask value where the cell may be SELECTED as a neighbour
+  // (CK.py:432-434: is_inside && mask > 0.5), else 0; the centre test (CK.py:426) needs the raw
+  // value, which only differs on the border ring, handled below.
+  int any_sel = 0;
+  for (int a = ty; a < A; a += 8) {
+    const int r = r0 - HL + a;
+    for (int b = tx; b < B; b += 32) {
+      const int cc = c0 - HL + b;
+      float u = 0.f, m = 0.f;
+      if (r >= 0 && r < W && cc >= 0 && cc < W) {
+        const int gi = r * W + cc;
+        u = __ldg(up + gi);
+        m = __fadd_rn(__ldg(valid + gi), __ldg(isup + gi));
+      }
+      const bool inside = r > 0 && r < W - 1 && cc > 0 && cc < W - 1;
+      s_up[a * B + b] = u;
+      // keep the raw mask in the low range [0,..) and tag non-selectable cells by negating (-m-1 <= -1)
+      s_mask[a * B + b] = inside ? m : -m - 1.f;
+      any_sel |= (inside && m > 0.5f);
     }
-    s_up[e] = u; s_mask[e] = m;
   }
-  __syncthreads();
-  for (int e = tid; e < DA * DB; e += blockDim.x) {
+  any_sel = __syncthreads_or(any_sel);
+  for (int e = tid; e < DA * DB; e += 256) {
     const int a = e / DB, b = e - a * DB;
     const int r = r0 - 3 + a, cc = c0 - 3 + b;
     float out = 0.f;
     if (r >= 0 && r < W && cc >= 0 && cc < W) {
-      if (cc - k >= 0 && cc + k <= W - 1) {      // no row wrap-around possible: shared-memory path
-        const int sa = a + k, sb = b + k;        // position in the staged planes (HL - 3 == k)
+      if (cc - K >= 0 && cc + K <= W - 1) {      // no row wrap-around possible: shared-memory path
+        const int sa = a + K, sb = b + K;        // position in the staged planes (HL - 3 == K)
         out = s_up[sa * B + sb];
-        if (s_mask[sa * B + sb] < 0.5f) {
-          float distance = 100.f, near_value = 0.f;
-          for (int dy = -k; dy <= k; dy++) {
-            const int rr = r + dy;
-            if (rr <= 0 || rr >= W - 1) continue;
-            for (int dx = -k; dx <= k; dx++) {
-              const int c2 = cc + dx;
-              if (c2 <= 0 || c2 >= W - 1) continue;
-              if (s_mask[(sa + dy) * B + sb + dx] > 0.5f && (float)(dx + dy) < distance) {
-                distance = (float)(dx + dy); near_value = s_up[(sa + dy) * B + sb + dx];
-              }
+        const float mc = s_mask[sa * B + sb];
+        const float raw = mc < 0.f ? -mc - 1.f : mc;
+        if (raw < 0.5f && any_sel) {
+          // first hit in (dx+dy ascending, dy ascending) order == the reference's strict-< scan
+          bool found = false;
+          for (int sd = -2 * K; sd <= 2 * K && !found; sd++) {
+            const int dlo = max(-K, sd - K), dhi = min(K, sd + K);
+            for (int dy = dlo; dy <= dhi; dy++) {
+              const int dx = sd - dy;
+              if (s_mask[(sa + dy) * B + sb + dx] > 0.5f) { out = s_up[(sa + dy) * B + sb + dx]; found = true; break; }
             }
           }
-          if (distance < 100.f) out = near_value;
         }
       } else {
         out = dilate_cell_global(c, up, valid, isup, r * W + cc);
@@ -372,8 +439,9 @@ k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, 
     s_dil[e] = out;
   }
   __syncthreads();
-  for (int e = tid; e < PT_Y * PT_X; e += blockDim.x) {
-    const int a = e / PT_X, b = e - a * PT_X;
+#pragma unroll
+  for (int half = 0; half < PT_Y / 8; half++) {
+    const int a = ty + half * 8, b = tx;
     const int r = r0 + a, cc = c0 + b;
     if (r >= W || cc >= W) continue;
     const int gi = r * W + cc;

@@ -67,8 +67,11 @@ class ShardedElevationMap:
         self.torch = torch
         self.static_offsets = static_offsets      # (my_offset, total) when every rank's count is fixed
         em = self.em
-        # run the library on torch's current stream so kernels and NCCL collectives are stream-ordered
-        em._check(em._L.emap_set_stream(em._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        # run the library on one explicit torch stream so that kernels and NCCL collectives are stream-ordered
+        # (the legacy default stream, handle 0, cannot be named through the C ABI)
+        cur = torch.cuda.current_stream()
+        self.stream = cur if cur.cuda_stream != 0 else torch.cuda.Stream()
+        em._check(em._L.emap_set_stream(em._h, C.c_void_p(self.stream.cuda_stream)))
         self._cache = {}
 
     def _exchange(self, phase):
@@ -110,6 +113,15 @@ class ShardedElevationMap:
         Rm = np.ascontiguousarray(np.stack([np.asarray(_to_host(r), np.float32).reshape(9) for r in Rs]))
         tm = np.ascontiguousarray(np.stack([np.asarray(_to_host(t), np.float32).reshape(3) for t in ts]))
         L, h = em._L, em._h
+        self.stream.wait_stream(self.torch.cuda.current_stream())
+        with self.torch.cuda.stream(self.stream):
+            self._frame(L, h, ns, ptrs, counts, stride, dt, device_ptrs, Rm, tm, off, position_noise, orientation_noise,
+                        overlap_z)
+        self.torch.cuda.current_stream().wait_stream(self.stream)
+
+    def _frame(self, L, h, ns, ptrs, counts, stride, dt, device_ptrs, Rm, tm, off, position_noise, orientation_noise,
+               overlap_z):
+        em = self.em
         em._check(L.emap_shard_begin(h, ns, ptrs, counts, stride, dt, int(bool(device_ptrs)), Rm.ctypes.data,
                                      tm.ctypes.data, off, float(position_noise), float(orientation_noise)))
         if overlap_z is not None:
