@@ -187,7 +187,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 
     param = core_parameter(1024)
-    em = ElevationMap(param, device=local_rank)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # stdout carries exactly one JSON line
+        em = ElevationMap(param, device=local_rank)
     frames = make_frames(world, rank, N_FRAME_POOL)
     frames0 = frames if rank == 0 or world == 1 else None
     sh = None

@@ -51,7 +51,11 @@ struct emap_handle {
   int in_sel = 0;
   float4* xyzv = nullptr;
   int* pidx = nullptr;
+  Ray* rays = nullptr;        // compacted rays of the frame, one segment per sensor (at the sensor's point offset)
+  int* ray_ctl = nullptr;     // per sensor: {ray count, work counter}
+  int ray_ctl_cap = 0;        // sensors
   i64 pt_cap = 0;
+  int n_sm = 148, rc_blocks_per_sm = 8;
   // last frame description
   std::vector<Pose> poses;
   std::vector<i64> offs;      // n_sensors + 1
@@ -129,6 +133,7 @@ void fill_devcfg(const emap_config& c, DevCfg& d) {
   d.c_out = (float)c.outlier_variance; d.init_var = (float)c.initial_variance;
   d.max_drift_f = (float)c.max_drift; d.drift_alpha_f = (float)c.drift_compensation_alpha;
   d.max_len16 = h16_host((float)c.max_ray_length);
+  d.w_plus_half_f = (float)c.cell_n + 0.5f;
   d.res_f = (float)c.resolution;
   d.overlap_z_f = (float)c.overlap_clear_range_z; d.time_var_f = (float)c.time_variance;
   d.time_int_f = (float)c.time_interval;
@@ -153,9 +158,11 @@ int ensure_points(emap_handle* h, i64 n) {
   CK(cudaStreamSynchronize(h->stream));
   if (h->xyzv) cudaFree(h->xyzv);
   if (h->pidx) cudaFree(h->pidx);
-  h->xyzv = nullptr; h->pidx = nullptr; h->pt_cap = 0;
+  if (h->rays) cudaFree(h->rays);
+  h->xyzv = nullptr; h->pidx = nullptr; h->rays = nullptr; h->pt_cap = 0;
   CK(cudaMalloc(&h->xyzv, sizeof(float4) * cap));
   CK(cudaMalloc(&h->pidx, sizeof(int) * cap));
+  CK(cudaMalloc(&h->rays, sizeof(Ray) * cap));
   h->pt_cap = cap;
   return 0;
 }
@@ -179,10 +186,11 @@ int stage_mark(emap_handle* h, int k) {
 }
 
 template <typename T>
-int launch_index(emap_handle* h, const Pose& q, const T* pts, i64 n, i64 stride, i64 off) {
+int launch_index(emap_handle* h, const Pose& q, const T* pts, i64 n, i64 stride, i64 off, int sensor) {
   if (n <= 0) return 0;
   k_index_error<T><<<cdiv(n, 256), 256, 0, h->stream>>>(h->dc, q, pts, n, stride, h->xyzv + off, h->pidx + off, h->map,
-                                                           h->sc.cnt_all, h->sc.cnt_inl, h->fs);
+                                                           h->sc.cnt_all, h->sc.cnt_inl, h->fs, h->rays + off,
+                                                           h->ray_ctl + 2 * sensor);
   LAUNCH_CHECK();
   return 0;
 }
@@ -210,7 +218,14 @@ int frame_begin(emap_handle* h, int32_t n_sensors, const void* const* points, co
     make_pose(R + 9 * s, tr, &h->poses[s]);
   }
   // frame scalars: keep mean / additive error, zero the accumulators
-  k_frame_reset<<<1, 32, 0, h->stream>>>(h->fs, h->poses[0].t[2], 1);
+  if (n_sensors > h->ray_ctl_cap) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->ray_ctl) cudaFree(h->ray_ctl);
+    h->ray_ctl = nullptr; h->ray_ctl_cap = 0;
+    CK(cudaMalloc(&h->ray_ctl, sizeof(int) * 2 * (n_sensors + 8)));
+    h->ray_ctl_cap = n_sensors + 8;
+  }
+  k_frame_reset<<<1, 32, 0, h->stream>>>(h->fs, h->poses[0].t[2], 1, h->ray_ctl, 2 * n_sensors);
   LAUNCH_CHECK();
   if (stage_mark(h, 0)) return EMAP_ERR_CUDA;
   const void* dev_pts[64];
@@ -237,8 +252,8 @@ int frame_begin(emap_handle* h, int32_t n_sensors, const void* const* points, co
     CK(cudaStreamWaitEvent(h->stream, h->copy_done, 0));
   }
   for (int s = 0; s < n_sensors; s++) {
-    rc = dtype == EMAP_F32 ? launch_index<float>(h, h->poses[s], (const float*)dp[s], n[s], row_stride, h->offs[s])
-                           : launch_index<double>(h, h->poses[s], (const double*)dp[s], n[s], row_stride, h->offs[s]);
+    rc = dtype == EMAP_F32 ? launch_index<float>(h, h->poses[s], (const float*)dp[s], n[s], row_stride, h->offs[s], s)
+                           : launch_index<double>(h, h->poses[s], (const double*)dp[s], n[s], row_stride, h->offs[s], s);
     if (rc) return rc;
   }
   if (!is_device_ptr) {
@@ -273,9 +288,14 @@ int frame_rays(emap_handle* h) {
     for (size_t s = 0; s + 1 < h->offs.size(); s++) {
       const i64 n = h->offs[s + 1] - h->offs[s];
       if (n <= 0 || h->dc.n_steps == 0) continue;
-      k_raycast<<<cdiv(n, RC_PTS), RC_PTS, sm, h->stream>>>(h->dc, h->poses[s], n, h->xyzv + h->offs[s],
-                                                             h->pidx + h->offs[s], h->map, h->normal, h->sc, h->steps,
-                                                             h->fs, h->count_rays);
+      // persistent grid: enough CTAs to fill every SM, never more than one warp per possible ray
+      const int grid = (int)std::min<i64>((i64)h->n_sm * h->rc_blocks_per_sm, (n + 3) / 4);
+      if (h->count_rays)
+        k_raycast<true><<<grid, RC_THREADS, sm, h->stream>>>(h->dc, h->poses[s], h->rays + h->offs[s], h->ray_ctl + 2 * s,
+                                                               h->map, h->normal, h->sc, h->steps, h->fs);
+      else
+        k_raycast<false><<<grid, RC_THREADS, sm, h->stream>>>(h->dc, h->poses[s], h->rays + h->offs[s], h->ray_ctl + 2 * s,
+                                                                h->map, h->normal, h->sc, h->steps, h->fs);
       LAUNCH_CHECK();
     }
   } else if (stage_mark(h, 4)) return EMAP_ERR_CUDA;
@@ -286,7 +306,8 @@ int frame_rays(emap_handle* h) {
 
 size_t post_smem(const DevCfg& d) {
   const int HL = d.dilation + 3;
-  return sizeof(float) * (size_t)(2 * (PT_Y + 2 * HL) * (PT_X + 2 * HL) + (PT_Y + 6) * (PT_X + 6));
+  return sizeof(float) * (size_t)(2 * (PT_Y + 2 * HL) * (PT_X + 2 * HL) + (PT_Y + 6) * (PT_X + 6) + 2)
+         + sizeof(unsigned long long) * (size_t)(PT_Y + 2 * HL);
 }
 
 int launch_post(emap_handle* h) {
@@ -369,6 +390,7 @@ int emap_create(const emap_config* cfg, int device, emap_handle** out) {
   fill_devcfg(*cfg, h->dc);
   build_steps(*cfg, h->dc.max_len16, h->steps_host);
   h->dc.n_steps = (int)h->steps_host.size();
+  h->dc.first_step = h->steps_host.empty() ? INFINITY : h->steps_host[0];
   const size_t C = (size_t)h->dc.C;
   if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   h->stream = h->own_stream;
@@ -414,8 +436,18 @@ int emap_create(const emap_config* cfg, int device, emap_handle** out) {
   h->launches++;
   if (post_smem(h->dc) > 48 * 1024)
     cudaFuncSetAttribute(k_post<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(h->dc));
-  if (sizeof(float) * (h->steps_host.size() + 32) > 40 * 1024)
-    cudaFuncSetAttribute(k_raycast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * (h->steps_host.size() + 32)));
+  {
+    const int sm_bytes = (int)(sizeof(float) * ((h->steps_host.size() + 31) & ~(size_t)31));
+    if (sm_bytes > 40 * 1024) {
+      cudaFuncSetAttribute(k_raycast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes);
+      cudaFuncSetAttribute(k_raycast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes);
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->n_sm = prop.multiProcessorCount;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_raycast<false>, RC_THREADS, sm_bytes) == cudaSuccess && nb > 0)
+      h->rc_blocks_per_sm = nb;
+  }
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail("init", e);
   if ((e = cudaGetLastError()) != cudaSuccess) return bail("init", e);
   *out = h;
@@ -429,7 +461,7 @@ int emap_destroy(emap_handle* h) {
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   void* ptrs[] = {h->map, h->map_alt, h->normal, h->trav_input, h->u32_block, h->i64_block, h->sc.last, h->sc.rec,
                   h->sc.ukv, h->ukey_x, h->fs, h->steps, h->d_export, h->d_in[0], h->d_in[1], h->xyzv, h->pidx, h->pl[0], h->pl[1],
-                  h->pl[2], h->pl[3], h->pl_cnt};
+                  h->pl[2], h->pl[3], h->pl_cnt, h->rays, h->ray_ctl};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int b = 0; b < 2; b++) if (h->in_free[b]) cudaEventDestroy(h->in_free[b]);
   if (h->copy_done) cudaEventDestroy(h->copy_done);
@@ -487,7 +519,7 @@ int emap_shard_begin(emap_handle* h, int32_t n_sensors, const void* const* point
 int emap_shard_set_overlap_z(emap_handle* h, float z_abs) {
   ENTER(h);
   if (h->phase < 1) return fail(h, EMAP_ERR_STATE, "emap_shard_set_overlap_z must follow emap_shard_begin");
-  k_frame_reset<<<1, 32, 0, h->stream>>>(h->fs, z_abs - h->center[2], 0);
+  k_frame_reset<<<1, 32, 0, h->stream>>>(h->fs, z_abs - h->center[2], 0, nullptr, 0);
   LAUNCH_CHECK();
   return EMAP_OK;
 }

@@ -42,6 +42,8 @@ struct DevCfg {
   double mvd2, max_height, ramp_a, ramp_b, ramp_c, max_variance;
   double pos_thresh, ori_thresh;
   float inv_res_f, half_w_f;   // fp32 estimate of the cell coordinate; exact path decides near integers
+  float w_plus_half_f;         // (float)W + 0.5f
+  float first_step;            // s_0 of the march table (+inf if the table is empty)
   float c_out;                 // (float)outlier_variance, the atomicAdd operand of CK.py:174,251
   float init_var, max_drift_f, drift_alpha_f, max_len16;
   float res_f;                 // CK.py:479-481 resolution() returns float
@@ -51,6 +53,11 @@ struct DevCfg {
 
 struct Pose {                  // one sensor: R and t rounded to fp16 where the reference does (CK.py:54-57,62-69,83-85)
   float R16[9], t16[3], t[3];
+};
+
+struct __align__(16) Ray {     // one valid point's ray: set up once (CK.py:83-101,199-201,250)
+  float x, y, z, len;          // end point (fp32) and fp16 march length
+  float rx, ry, rz, len_far;   // fp16 unit direction; samples with s < len_far are provably > sqrt(0.1) m from the end point
 };
 
 struct FrameScalars {          // device-resident scalars of the running frame
@@ -85,21 +92,30 @@ __device__ __forceinline__ float funkey(u32 k) {
 }
 
 // CK.py:26-33 + 22-25: clamp(int((c16 - 0)/resolution + 0.5*W), 0, W-1) for an fp16-valued c16.
-// The reference evaluates the quotient in double; the fp32 estimate q is within 2.5e-4 of it
-// for every |q| <= W+1 <= 2050 (|c16|/res * 2^-24 + ulp(2048)/2), so it decides the truncation
-// unless q is within 1e-3 of an integer; those (and non-finite inputs) take the double path.
+// The reference evaluates the quotient in double and truncates toward zero.  The fp32 estimate q is
+// within 2.5e-4 of it for every |q| <= W+1 <= 2050 (|c16|/res * 2^-24 + ulp(2048)/2), so floor(q)
+// decides the cell unless q is within 1e-3 of an integer; those take the double path.  q is first
+// clamped to [-0.5, W+0.5] (NaN -> -0.5): everything below 0 clamps to cell 0 and everything above W-1
+// to W-1 anyway, and floor == trunc for the in-range values.
 __device__ __forceinline__ int axis_cell(const DevCfg& c, float c16) {
-  float q = fmaf(c16, c.inv_res_f, c.half_w_f);
-  if (q < -0.5f) return 0;
-  if (q > (float)c.W + 0.5f) return c.W - 1;
-  float fr = q - floorf(q);
-  int i;
-  if (fr > 1e-3f && fr < 1.0f - 1e-3f) {
-    i = (int)q;                                  // q >= -0.5 here; (int) truncates like cvt.rzi
-  } else {
-    i = __double2int_rz((double)c16 / c.resolution + c.half_w);   // also the NaN path (-> 0)
-  }
+  const float q = fminf(fmaxf(fmaf(c16, c.inv_res_f, c.half_w_f), -0.5f), c.w_plus_half_f);
+  const float fl = floorf(q);
+  int i = (int)fl;
+  if (fabsf((q - fl) - 0.5f) > 0.499f) i = __double2int_rz((double)c16 / c.resolution + c.half_w);
   return min(max(i, 0), c.W - 1);                // fp16 clamp is exact for W-1 <= 2048
+}
+
+// both axes with ONE rare branch for the exact path
+__device__ __forceinline__ void axis_cell2(const DevCfg& c, float x16, float y16, int& ix, int& iy) {
+  const float qx = fminf(fmaxf(fmaf(x16, c.inv_res_f, c.half_w_f), -0.5f), c.w_plus_half_f);
+  const float qy = fminf(fmaxf(fmaf(y16, c.inv_res_f, c.half_w_f), -0.5f), c.w_plus_half_f);
+  const float fx = floorf(qx), fy = floorf(qy);
+  ix = (int)fx; iy = (int)fy;
+  if (fmaxf(fabsf((qx - fx) - 0.5f), fabsf((qy - fy) - 0.5f)) > 0.499f) {
+    ix = __double2int_rz((double)x16 / c.resolution + c.half_w);
+    iy = __double2int_rz((double)y16 / c.resolution + c.half_w);
+  }
+  ix = min(max(ix, 0), c.W - 1); iy = min(max(iy, 0), c.W - 1);
 }
 
 // CK.py:34-44

@@ -37,9 +37,11 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64 n, const i64 stride,
               float4* __restrict__ xyzv, int* __restrict__ pidx, const float* __restrict__ map,
-              u32* __restrict__ cnt_all, u32* __restrict__ cnt_inl, FrameScalars* fs) {
+              u32* __restrict__ cnt_all, u32* __restrict__ cnt_inl, FrameScalars* fs,
+              Ray* __restrict__ rays, int* __restrict__ ray_ctl) {
   const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   i64 e = 0; int ec = 0, nv = 0;
+  Ray ray; ray.len = -1.f;
   if (i < n) {
     const T* p = pts + i * stride;
     float px = (float)p[0], py = (float)p[1], pz = (float)p[2];   // EM.py:456 cast to fp32
@@ -53,6 +55,23 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
       rec = idx | (g.valid ? PT_VALID : 0) | (g.inside ? PT_INSIDE : 0);
       o = make_float4(g.x, g.y, g.z, g.v);
       nv = g.valid;
+      if (g.valid && c.visibility) {
+        // ray_vector CK.py:83-101 and the per-ray constants of CK.py:199-201,250
+        const float vx = h16(h16(g.x) - q.t16[0]), vy = h16(h16(g.y) - q.t16[1]), vz = h16(h16(g.z) - q.t16[2]);
+        const float norm = h16(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz))));
+        ray.rx = ray.ry = ray.rz = 0.f;
+        if (norm > 0.f) { ray.rx = h16(__fdiv_rn(vx, norm)); ray.ry = h16(__fdiv_rn(vy, norm)); ray.rz = h16(__fdiv_rn(vz, norm)); }
+        ray.x = g.x; ray.y = g.y; ray.z = g.z;
+        ray.len = fminf(norm, c.max_len16);                       // CK.py:201
+        // Bound used to skip the `d < 0.1` test of CK.py:225-226 far from the end point p.  With u = p - t,
+        // the fp16 roundings of p, t and their difference move v by at most sqrt(3)*2^-11*(2m + |v|) (m = largest
+        // coordinate magnitude), the fp16 direction and norm by at most 9.2e-4*s, and |v| >= norm*(1 - 2^-11), so
+        // |p - (t + dir*s)| >= (norm - s)(1 - 2^-11) - 1e-3*(2m + 2 norm).  d >= 0.1003 (no fp16 rounding can
+        // bring it under 0.1) is therefore guaranteed for s < norm - (0.325 + 1e-3*(2m + 2 norm)).
+        const float m = fmaxf(fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fabsf(g.z)),
+                              fmaxf(fmaxf(fabsf(q.t[0]), fabsf(q.t[1])), fabsf(q.t[2])));
+        ray.len_far = norm - (0.325f + 1e-3f * (2.f * m + 2.f * norm));
+      }
       if (g.valid && g.inside) {                                  // CK.py:318-323
         const float mh = __ldg(map + idx), mv = __ldg(map + c.C + idx);
         const float mvalid = __ldg(map + 2 * c.C + idx), mt = __ldg(map + 3 * c.C + idx);
@@ -65,6 +84,23 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
       }
     }
     xyzv[i] = o; pidx[i] = rec;
+  }
+  // compact the rays that have at least one march step (s_0 < len) into the sensor's ray list:
+  // one atomic per warp; the list order is irrelevant (every ray effect is a commutative integer atomic)
+  {
+    const bool has = ray.len > c.first_step;
+    const u32 bal = __ballot_sync(0xffffffffu, has);
+    if (bal) {
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(ray_ctl, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (has) {
+        float4* dst = reinterpret_cast<float4*>(rays + base + __popc(bal & ((1u << lane) - 1u)));
+        dst[0] = make_float4(ray.x, ray.y, ray.z, ray.len);
+        dst[1] = make_float4(ray.rx, ray.ry, ray.rz, ray.len_far);
+      }
+    }
   }
   // block reduction -> one integer atomic per block (order independent)
   for (int o = 16; o > 0; o >>= 1) {
@@ -85,7 +121,8 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
 }
 
 // start of a frame: zero the accumulators (keep mean / additive error), set the overlap-clear reference
-__global__ void k_frame_reset(FrameScalars* fs, float overlap_tz, int zero) {
+__global__ void k_frame_reset(FrameScalars* fs, float overlap_tz, int zero, int* ray_ctl, int n_ctl) {
+  if (zero) for (int k = threadIdx.x; k < n_ctl; k += blockDim.x) ray_ctl[k] = 0;
   if (threadIdx.x || blockIdx.x) return;
   if (zero) { fs->E = 0; fs->ecnt = 0; fs->nvalid = 0; fs->ray_steps = 0; fs->ray_visits = 0; }
   fs->overlap_tz = overlap_tz;
@@ -171,81 +208,64 @@ k_record(const DevCfg c, const float* __restrict__ map, const CellScratch s, con
   s.rec[i] = make_uint2(a, fl);
 }
 
-// CK.py:198-259 ray-cast half.  A CTA owns RC_PTS consecutive points: every thread sets up the ray of
-// one point (CK.py:83-101,199-201), the valid rays are compacted in shared memory, then each WARP
-// marches one ray at a time with its 32 lanes on 32 consecutive steps of the fp16 march variable
-// s_k (shared table: s_0 = half(step), s_{k+1} = half(float(double(s_k) + step)), CK.py:203).
+// CK.py:198-259 ray-cast half as a persistent kernel.  The rays of the frame were set up and compacted
+// by k_index_error; every WARP pulls the next ray from a global work counter (dynamic balancing: ray
+// lengths differ by 100x) and marches it with its 32 lanes on 32 consecutive steps of the fp16 march
+// variable s_k (shared table: s_0 = half(step), s_{k+1} = half(float(double(s_k) + step)), CK.py:203).
 // "Same cell as the previous step" (CK.py:209-210) is a shuffle with the neighbouring lane.  The
-// effects of a visit are commutative integer atomics, so the lane order is irrelevant.
-#define RC_PTS 128
-__global__ void __launch_bounds__(RC_PTS)
-k_raycast(const DevCfg c, const Pose q, const i64 n, const float4* __restrict__ xyzv,
-          const int* __restrict__ pidx, const float* __restrict__ map, const float* __restrict__ normal,
-          const CellScratch s, const float* __restrict__ steps, FrameScalars* fs, const int count) {
+// effects of a visit are commutative integer atomics, so neither lane nor ray order matters.
+#define RC_THREADS 128
+template <bool COUNT>
+__global__ void __launch_bounds__(RC_THREADS)
+k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __restrict__ ray_ctl,
+          const float* __restrict__ map, const float* __restrict__ normal,
+          const CellScratch s, const float* __restrict__ steps, FrameScalars* fs) {
   extern __shared__ float s_steps[];             // n_steps padded to a multiple of 32 with +inf
-  __shared__ float s_p[7][RC_PTS];
-  __shared__ i64 s_dec[RC_PTS];
-  __shared__ int s_wc[RC_PTS / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int n_pad = (c.n_steps + 31) & ~31;
-  for (int k = tid; k < n_pad; k += RC_PTS) s_steps[k] = steps[k];
-  const i64 i = blockIdx.x * (i64)RC_PTS + tid;
-  bool ok = false;
-  float x = 0.f, y = 0.f, z = 0.f, rx = 0.f, ry = 0.f, rz = 0.f, len = 0.f;
-  i64 dec_fix = 0;
-  if (i < n) {
-    const int prec = pidx[i];
-    ok = (prec & (PT_VALID | PT_SKIP)) == PT_VALID;               // CK.py:226: invalid points do nothing
-    if (ok) {
-      const float4 g = xyzv[i];
-      x = g.x; y = g.y; z = g.z;
-      // ray_vector CK.py:83-101
-      const float vx = h16(h16(x) - q.t16[0]), vy = h16(h16(y) - q.t16[1]), vz = h16(h16(z) - q.t16[2]);
-      const float norm = h16(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz))));
-      if (norm > 0.f) { rx = h16(__fdiv_rn(vx, norm)); ry = h16(__fdiv_rn(vy, norm)); rz = h16(__fdiv_rn(vz, norm)); }
-      len = fminf(norm, c.max_len16);                             // CK.py:201
-      dec_fix = fix32((float)(-c.cleanup_step / ((double)len / c.max_ray_length)));   // CK.py:250
-    }
-  }
-  const u32 bal = __ballot_sync(0xffffffffu, ok);
-  if (lane == 0) s_wc[warp] = __popc(bal);
+  for (int k = tid; k < n_pad; k += RC_THREADS) s_steps[k] = steps[k];
   __syncthreads();
-  int base = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < RC_PTS / 32; w++) { if (w < warp) base += s_wc[w]; total += s_wc[w]; }
-  if (ok) {
-    const int pos = base + __popc(bal & ((1u << lane) - 1u));
-    s_p[0][pos] = x; s_p[1][pos] = y; s_p[2][pos] = z; s_p[3][pos] = rx; s_p[4][pos] = ry; s_p[5][pos] = rz;
-    s_p[6][pos] = len; s_dec[pos] = dec_fix;
-  }
-  __syncthreads();
+  const int n_rays = ray_ctl[0];
+  int* next = ray_ctl + 1;
   const int W = c.W, C = c.C;
   const float tx = q.t[0], ty = q.t[1], tz = q.t[2];
   int n_steps_done = 0, n_visits = 0;
-  for (int r = warp; r < total; r += RC_PTS / 32) {
-    x = s_p[0][r]; y = s_p[1][r]; z = s_p[2][r]; rx = s_p[3][r]; ry = s_p[4][r]; rz = s_p[5][r]; len = s_p[6][r];
-    dec_fix = s_dec[r];
+  int pend = 0;
+  if (lane == 0) pend = atomicAdd(next, 1);
+  int r = __shfl_sync(0xffffffffu, pend, 0);
+  while (r < n_rays) {
+    if (lane == 0) pend = atomicAdd(next, 1);                     // next ray: latency hidden by this march
+    const float4 ra = __ldg(reinterpret_cast<const float4*>(rays + r));
+    const float4 rb = __ldg(reinterpret_cast<const float4*>(rays + r) + 1);
+    const float x = ra.x, y = ra.y, z = ra.z, len = ra.w, rx = rb.x, ry = rb.y, rz = rb.z;
+    const i64 dec_fix = fix32((float)(-c.cleanup_step / ((double)len / c.max_ray_length)));   // CK.py:250
+    const float len_far = rb.w;
     int carry = -1;
     for (int kb = 0; kb < n_pad; kb += 32) {
-      if (!(s_steps[kb] < len)) break;                            // warp-uniform
       const float sk = s_steps[kb + lane];
       const bool act = sk < len;
+      if (!__any_sync(0xffffffffu, act)) break;
       const float nx = __fmaf_rn(rx, sk, tx);                     // t + ray*s: product exact (CK.py:205-207)
       const float ny = __fmaf_rn(ry, sk, ty);
-      const int ix = axis_cell(c, h16(nx)), iy = axis_cell(c, h16(ny));
+      int ix, iy;
+      axis_cell2(c, h16(nx), h16(ny), ix, iy);
       const int nidx = act ? ix * W + iy : -2;
       int prev = __shfl_up_sync(0xffffffffu, nidx, 1);
       if (lane == 0) prev = carry;
       carry = __shfl_sync(0xffffffffu, nidx, 31);
-      if (count) n_steps_done += act;
-      if (!act || nidx == prev) continue;                         // CK.py:209
+      if (COUNT) n_steps_done += act;
+      if (nidx == prev || !act) continue;                         // CK.py:209
       if (!cell_inside(W, ix, iy)) continue;                      // CK.py:211
       const float nz = __fmaf_rn(rz, sk, tz);
-      const float ddx = x - nx, ddy = y - ny, ddz = z - nz;
-      float d = __fmul_rn(ddy, ddy); d = __fmaf_rn(ddx, ddx, d); d = __fmaf_rn(ddz, ddz, d);   // CK.py:225
-      d = h16(d);
-      if (d < 0.1f) continue;      // CK.py:226 `d < 0.1` in double: no fp16 value lies in [0.1, 0.1f)
-      if (count) n_visits++;
+      // CK.py:225-226 `d < 0.1` (d = fp16 of the squared distance to the end point) cannot fire for
+      // s < len_far (bound derived where the ray is set up, k_index_error).
+      if (!(sk < len_far)) {
+        const float ddx = x - nx, ddy = y - ny, ddz = z - nz;
+        float d = __fmul_rn(ddy, ddy); d = __fmaf_rn(ddx, ddx, d); d = __fmaf_rn(ddz, ddz, d);
+        d = h16(d);
+        if (d < 0.1f) continue;    // `d < 0.1` in double: no fp16 value lies in [0.1, 0.1f)
+      }
+      if (COUNT) n_visits++;
       const uint2 rc = s.rec[nidx];
       if (!(rc.y & RF_VALID)) {                                   // CK.py:229-235 carve the upper bound
         const u32 key = fkey(nz);
@@ -267,8 +287,9 @@ k_raycast(const DevCfg c, const Pose q, const i64 n, const float4* __restrict__ 
       atomicAdd(s.n_ray + nidx, 1u);                              // CK.py:251
       atomicMin(s.ukv + nidx, fkey(nz));                          // CK.py:253-256
     }
+    r = __shfl_sync(0xffffffffu, pend, 0);
   }
-  if (count) {
+  if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       n_steps_done += __shfl_down_sync(0xffffffffu, n_steps_done, o);
       n_visits += __shfl_down_sync(0xffffffffu, n_visits, o);
@@ -352,20 +373,22 @@ k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const F
 #define PT_X 32
 #define PT_Y 16
 
-// exact flat-index semantics of CK.py:403-418,429-438 for one cell, from global memory
-// (only used for the K-1 outermost columns on each side, where a window wraps into the adjacent row)
+// exact flat-index semantics of CK.py:403-418,429-438 for one cell, from global memory: the neighbour
+// offset (dx,dy) is applied to the FLAT index, so a window that leaves the row on the left / right
+// continues in the previous / next row.  Only cells within K-2 columns of the left or right edge can
+// select such a wrapped neighbour (the wrapped column must itself be inside), so only they come here.
 __device__ float dilate_cell_global(const DevCfg& c, const float* __restrict__ up, const float* __restrict__ valid,
-                                    const float* __restrict__ isup, int i) {
-  const int W = c.W, k = c.dilation;
+                                    const float* __restrict__ isup, int r, int cc) {
+  const int W = c.W, k = c.dilation, i = r * W + cc;
   const float h = up[i];
   if (__fadd_rn(valid[i], isup[i]) >= 0.5f) return h;
   float distance = 100.f, near_value = 0.f;
   for (int dy = -k; dy <= k; dy++)
     for (int dx = -k; dx <= k; dx++) {
-      const int idx = i + W * dy + dx;
-      if (idx < 0 || idx >= c.C) continue;
-      const int ix = idx / W, iy = idx % W;
-      if (ix <= 0 || ix >= W - 1 || iy <= 0 || iy >= W - 1) continue;
+      int rr = r + dy, c2 = cc + dx;
+      if (c2 < 0) { c2 += W; rr -= 1; } else if (c2 >= W) { c2 -= W; rr += 1; }   // idx / W, idx % W of CK.py:409-410
+      if (rr <= 0 || rr >= W - 1 || c2 <= 0 || c2 >= W - 1) continue;
+      const int idx = rr * W + c2;
       if (__fadd_rn(valid[idx], isup[idx]) > 0.5f && (float)(dx + dy) < distance) {
         distance = (float)(dx + dy); near_value = up[idx];
       }
@@ -384,31 +407,35 @@ k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, 
   const int A = PT_Y + 2 * HL, B = PT_X + 2 * HL;
   constexpr int DA = PT_Y + 6, DB = PT_X + 6;
   float* s_up = smem;                            // A*B   upper_bound
-  float* s_mask = s_up + A * B;                  // A*B   selectable neighbour: inside && is_valid + is_upper_bound > 0.5
+  float* s_mask = s_up + A * B;                  // A*B   raw mask = is_valid + is_upper_bound (CK.py:424)
   float* s_dil = s_mask + A * B;                 // DA*DB dilated tile (+3 halo)
+  unsigned long long* s_rowsel = reinterpret_cast<unsigned long long*>(s_dil + DA * DB + ((DA * DB) & 1));   // A words
   const float* up = map + 5 * C; const float* valid = map + 2 * C; const float* isup = map + 6 * C;
   const int r0 = blockIdx.y * PT_Y, c0 = blockIdx.x * PT_X;
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  // stage: s_mask holds the raw mask value where the cell may be SELECTED as a neighbour
-  // (CK.py:432-434: is_inside && mask > 0.5), else 0; the centre test (CK.py:426) needs the raw
-  // value, which only differs on the border ring, handled below.
+  // stage the two planes; per staged row also one 64-bit word whose bit b says "cell (a,b) may be
+  // SELECTED as a neighbour" (CK.py:432-434: is_inside && mask > 0.5), built with warp ballots (B <= 64)
   int any_sel = 0;
   for (int a = ty; a < A; a += 8) {
     const int r = r0 - HL + a;
-    for (int b = tx; b < B; b += 32) {
+    u32 bits[2];
+#pragma unroll
+    for (int ch = 0; ch < 2; ch++) {
+      const int b = tx + 32 * ch;
       const int cc = c0 - HL + b;
       float u = 0.f, m = 0.f;
-      if (r >= 0 && r < W && cc >= 0 && cc < W) {
+      const bool in_stage = b < B;
+      if (in_stage && r >= 0 && r < W && cc >= 0 && cc < W) {
         const int gi = r * W + cc;
         u = __ldg(up + gi);
         m = __fadd_rn(__ldg(valid + gi), __ldg(isup + gi));
       }
-      const bool inside = r > 0 && r < W - 1 && cc > 0 && cc < W - 1;
-      s_up[a * B + b] = u;
-      // keep the raw mask in the low range [0,..) and tag non-selectable cells by negating (-m-1 <= -1)
-      s_mask[a * B + b] = inside ? m : -m - 1.f;
-      any_sel |= (inside && m > 0.5f);
+      const bool sel = in_stage && r > 0 && r < W - 1 && cc > 0 && cc < W - 1 && m > 0.5f;
+      if (in_stage) { s_up[a * B + b] = u; s_mask[a * B + b] = m; }
+      bits[ch] = __ballot_sync(0xffffffffu, sel);
     }
+    if (tx == 0) s_rowsel[a] = ((unsigned long long)bits[1] << 32) | bits[0];
+    any_sel |= (bits[0] | bits[1]) != 0;
   }
   any_sel = __syncthreads_or(any_sel);
   for (int e = tid; e < DA * DB; e += 256) {
@@ -416,24 +443,34 @@ k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, 
     const int r = r0 - 3 + a, cc = c0 - 3 + b;
     float out = 0.f;
     if (r >= 0 && r < W && cc >= 0 && cc < W) {
-      if (cc - K >= 0 && cc + K <= W - 1) {      // no row wrap-around possible: shared-memory path
+      if (cc >= K - 1 && cc <= W - K) {          // no wrapped neighbour can be selected: shared-memory path
         const int sa = a + K, sb = b + K;        // position in the staged planes (HL - 3 == K)
         out = s_up[sa * B + sb];
-        const float mc = s_mask[sa * B + sb];
-        const float raw = mc < 0.f ? -mc - 1.f : mc;
-        if (raw < 0.5f && any_sel) {
-          // first hit in (dx+dy ascending, dy ascending) order == the reference's strict-< scan
-          bool found = false;
-          for (int sd = -2 * K; sd <= 2 * K && !found; sd++) {
-            const int dlo = max(-K, sd - K), dhi = min(K, sd + K);
-            for (int dy = dlo; dy <= dhi; dy++) {
-              const int dx = sd - dy;
-              if (s_mask[(sa + dy) * B + sb + dx] > 0.5f) { out = s_up[(sa + dy) * B + sb + dx]; found = true; break; }
+        if (any_sel && s_mask[sa * B + sb] < 0.5f) {
+          // windows of selectable neighbours, one (2K+1)-bit word per row; first hit in
+          // (dx+dy ascending, dy ascending) order == the reference's strict-< scan (CK.py:429-438)
+          // Row dy's (2K+1)-bit window of selectable neighbours, shifted left by (dy+K), puts the
+          // neighbour (dy,dx) at bit s' = (dx+K)+(dy+K): the reference's strict-< scan (CK.py:429-438)
+          // picks the smallest dx+dy, ties to the smallest dy == lowest set bit of the OR, then the
+          // first row that has it.  Branch-free, all lanes.
+          const u32 wmask = (1u << (2 * K + 1)) - 1u;
+          u32 any = 0;
+#pragma unroll
+          for (int dy = -K; dy <= K; dy++)
+            any |= ((u32)(s_rowsel[sa + dy] >> (sb - K)) & wmask) << (dy + K);
+          if (any) {
+            const int sp = __ffs(any) - 1;                       // s' of the winner
+            int dyw = K;
+#pragma unroll
+            for (int dy = K; dy >= -K; dy--) {
+              const int dx = sp - (dy + K) - K;
+              if (dx >= -K && dx <= K && ((s_rowsel[sa + dy] >> (sb + dx)) & 1ull)) dyw = dy;
             }
+            out = s_up[(sa + dyw) * B + sb + (sp - (dyw + K) - K)];
           }
         }
       } else {
-        out = dilate_cell_global(c, up, valid, isup, r * W + cc);
+        out = dilate_cell_global(c, up, valid, isup, r, cc);
       }
     }
     s_dil[e] = out;

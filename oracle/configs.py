@@ -26,6 +26,7 @@ def _default202():
 
 NAMED_PARAMS = {
     "default202": _default202,                      # dataclass defaults, 8 m / 0.04 m -> 202^2 (reference test shape)
+    "core130": lambda: core_parameter(130),         # small map for the committed golden fixtures
     "core202": lambda: core_parameter(202),         # deployed core_param.yaml values
     "core256": lambda: core_parameter(256),         # BASELINE config A
     "core512": lambda: core_parameter(512),         # BASELINE config E

@@ -126,3 +126,65 @@ def test_config_b_single_frame(oracle_mod):
             m.update_time()
     state, normal = em.get_state()
     compare_state(state, normal, om, label="config B")
+
+
+def test_engine_matches_committed_golden(oracle_mod):
+    """tests/golden/frames_core130.npz: outputs of the REFERENCE'S OWN kernel source (order-independent cells)
+    and of the oracle, generated in the build container by tests/golden/make_golden.py."""
+    import os
+    from elevation_mapping_cupy_b200.parameter import core_parameter, Parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "frames_core130.npz"))
+    p = core_parameter(130)
+    em = _mk(p)
+    for f in range(4):
+        pts, R, t = wl.lidar_cloud(0, f, n_rings=24, n_az=500, max_range=4.0)
+        em.move_to(t, R)
+        em.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+        state, normal = em.get_state()
+        for li in (0, 1, 2, 4, 5, 6):
+            assert np.array_equal(state[li], g[f"oracle_state_{f}"][li]), (f, li)
+            d = np.abs(state[li] - g[f"ref_state_{f}"][li])
+            assert d[~g[f"racy_{f}"]].max() <= 1e-6, (f, li)      # vs the reference source: 1e-6 << 1e-4 (BASELINE)
+        assert np.abs(state[3] - g[f"oracle_state_{f}"][3]).max() <= 2e-6
+        assert np.array_equal(normal, g[f"oracle_normal_{f}"])
+        idx, _, _ = em.get_point_record(len(pts))
+        assert np.array_equal(idx, g[f"ref_point_idx_{f}"])       # bit-identical cell indices vs the reference
+        em.update_variance(); em.update_time()
+    for seed in (0, 1):
+        gi = np.load(os.path.join(gold, f"index_default202_seed{seed}.npz"))
+        pd = Parameter(); pd.update()
+        e2 = _mk(pd)
+        pts, R, t = wl.reference_test_cloud(seed, n=20000)
+        if seed % 2:
+            pts = (pts * np.float32(9.0) - np.float32(4.5)).astype(np.float32)
+        e2.input_pointcloud(pts, ["x", "y", "z"], R, t, 0, 0)
+        idx, valid, inside = e2.get_point_record(len(pts))
+        assert np.array_equal(idx, gi["idx"]) and np.array_equal(valid, gi["valid"]) and np.array_equal(inside, gi["inside"])
+
+
+@pytest.mark.parametrize("cell_n,dil", [(130, 3), (202, 2), (130, 1), (202, 5)])
+def test_post_chain_on_random_state(oracle_mod, cell_n, dil):
+    """dilation (incl. the flat-index row wrap of CK.py:403-407) + CNN + normals on a random state, driven by
+    an empty cloud; border columns are populated on purpose."""
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    p = core_parameter(cell_n, dilation_size=dil, enable_visibility_cleanup=(dil != 2))
+    em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+    rng = np.random.default_rng(cell_n + dil)
+    W = cell_n
+    st = np.zeros((7, W, W), np.float32)
+    st[0] = rng.standard_normal((W, W)); st[1] = 0.05
+    st[2] = (rng.random((W, W)) < 0.2); st[2][:, :5] = rng.random((W, 5)) < 0.7; st[2][:, -5:] = rng.random((W, 5)) < 0.7
+    st[3] = 1.0; st[4] = 1.0
+    st[5] = rng.standard_normal((W, W)); st[6] = (rng.random((W, W)) < 0.1) * (st[2] < 0.5)
+    st[0] *= st[2]
+    em.set_state(st); om.elevation_map = st.copy()
+    empty = np.zeros((0, 3), np.float32)
+    R = np.eye(3, dtype=np.float32); t = np.array([0, 0, 1.0], np.float32)
+    em.input_pointcloud(empty, ["x", "y", "z"], R, t, 0.0, 0.0)
+    om.input_pointcloud(empty, ["x", "y", "z"], R, t, 0.0, 0.0)
+    state, normal = em.get_state()
+    compare_state(state, normal, om, label=f"post {cell_n}/{dil}")
+    ti = em.traversability_input.cpu().numpy()
+    assert np.array_equal(ti, om.traversability_input)

@@ -1,0 +1,142 @@
+"""CPU tests of the oracle (no GPU): the C restatement against (1) the committed golden vectors produced
+by the REFERENCE'S OWN kernel source, (2) an independent NumPy restatement of the index arithmetic,
+(3) the live reference source when oracle/_ref is buildable here (i.e. /root/reference exists)."""
+import os
+
+import numpy as np
+import pytest
+
+from elevation_mapping_cupy_b200 import workloads as wl
+from elevation_mapping_cupy_b200.parameter import Parameter, core_parameter
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_point_index_matches_reference_golden(oracle_mod, seed):
+    """bit-identical (idx, valid, inside) vs the reference kernel's write-back (CK.py:260-262)"""
+    g = np.load(os.path.join(GOLD, f"index_default202_seed{seed}.npz"))
+    p = Parameter(); p.update()
+    pts, R, t = wl.reference_test_cloud(seed, n=20000)
+    if seed % 2:
+        pts = (pts * np.float32(9.0) - np.float32(4.5)).astype(np.float32)
+    idx, valid, inside, _ = oracle_mod.point_index(p, pts, R, t)
+    assert np.array_equal(idx, g["idx"])
+    assert np.array_equal(valid, g["valid"])
+    assert np.array_equal(inside, g["inside"])
+    # independent NumPy restatement of the same arithmetic
+    ni, nv, nin = oracle_mod.point_index_numpy(p, pts, R, t)
+    assert np.array_equal(ni, idx) and np.array_equal(nv, valid) and np.array_equal(nin, inside)
+
+
+def test_index_numpy_vs_c_on_large_map(oracle_mod):
+    p = core_parameter(2048)
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-45, 45, (50000, 3)).astype(np.float32)
+    R = np.eye(3, dtype=np.float32); t = np.array([0.3, -0.2, 1.0], np.float32)
+    a = oracle_mod.point_index(p, pts, R, t)
+    b = oracle_mod.point_index_numpy(p, pts, R, t)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_frames_match_reference_golden(oracle_mod):
+    """4 LiDAR frames on a 130^2 map: the oracle's state equals (a) its own committed output exactly and
+    (b) the reference kernel source's output to 1e-6 on every cell whose outcome is order-independent."""
+    g = np.load(os.path.join(GOLD, "frames_core130.npz"))
+    p = core_parameter(130)
+    om = oracle_mod.OracleElevationMap(p)
+    for f in range(4):
+        pts, R, t = wl.lidar_cloud(0, f, n_rings=24, n_az=500, max_range=4.0)
+        om.move_to(t, R)
+        om.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+        for li in (0, 1, 2, 4, 5, 6):
+            assert np.array_equal(om.elevation_map[li], g[f"oracle_state_{f}"][li]), (f, li)
+        assert np.abs(om.elevation_map[3] - g[f"oracle_state_{f}"][3]).max() < 1e-6
+        assert np.array_equal(om.normal_map, g[f"oracle_normal_{f}"])
+        racy = g[f"racy_{f}"]
+        assert racy.mean() < 0.05
+        for li in (0, 1, 2, 4, 5, 6):
+            d = np.abs(om.elevation_map[li] - g[f"ref_state_{f}"][li])
+            assert d[~racy].max() <= 1e-6, (f, li, d[~racy].max())
+        assert np.array_equal(om.last_point_record[0], g[f"ref_point_idx_{f}"])
+        om.update_variance(); om.update_time()
+
+
+def test_oracle_threads_are_deterministic(oracle_mod):
+    p = core_parameter(130)
+    a = oracle_mod.OracleElevationMap(p, nthreads=1); b = oracle_mod.OracleElevationMap(p, nthreads=4)
+    for f in range(2):
+        pts, R, t = wl.lidar_cloud(0, f, n_rings=24, n_az=500, max_range=4.0)
+        for m in (a, b):
+            m.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02); m.update_time()
+    assert np.array_equal(a.elevation_map, b.elevation_map)
+    assert np.array_equal(a.normal_map, b.normal_map)
+
+
+def test_multi_sensor_equals_concatenation_when_poses_equal(oracle_mod):
+    p = core_parameter(130)
+    a = oracle_mod.OracleElevationMap(p); b = oracle_mod.OracleElevationMap(p)
+    pts, R, t = wl.lidar_cloud(0, 0, n_rings=24, n_az=500, max_range=4.0)
+    a.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.0, 0.0)
+    b.input_sensors([pts[:5000], pts[5000:]], [R, R], [t, t], 0.0, 0.0)
+    assert np.array_equal(a.elevation_map, b.elevation_map)
+
+
+def test_traversability_matches_torch_cpu(oracle_mod):
+    """traversability_filter.py:15-42 on the host with torch vs the oracle's direct convolution"""
+    torch = pytest.importorskip("torch")
+    p = core_parameter(130)
+    rm_w = oracle_mod.load_weights(p)
+    x = np.random.default_rng(0).standard_normal((130, 130)).astype(np.float32)
+    ours = oracle_mod.traversability(130, x, rm_w)
+    import torch.nn.functional as F
+    w1, w2, w3, wo = [torch.from_numpy(w) for w in rm_w]
+    e = torch.from_numpy(x).view(1, 1, 130, 130)
+    o1 = F.conv2d(e, w1.view(4, 1, 3, 3), dilation=1)[:, :, 2:-2, 2:-2]
+    o2 = F.conv2d(e, w2.view(4, 1, 3, 3), dilation=2)[:, :, 1:-1, 1:-1]
+    o3 = F.conv2d(e, w3.view(4, 1, 3, 3), dilation=3)
+    ref = torch.exp(-F.conv2d(torch.cat((o1, o2, o3), 1).abs(), wo.view(1, 12, 1, 1)))[0, 0].numpy()
+    assert np.abs(ours - ref).max() < 2e-6
+
+
+def test_smooth_matches_scipy(oracle_mod):
+    from scipy import ndimage
+    x = np.random.default_rng(1).standard_normal((202, 202)).astype(np.float32)
+    ours = oracle_mod.smooth(202, x)
+    ref = ndimage.uniform_filter(ndimage.uniform_filter(x, size=3), size=3)     # smooth_filter.py:57-58
+    assert np.abs(ours - ref).max() < 1e-6
+
+
+def test_dilation_and_normal_against_reference_source(oracle_mod):
+    """live pin against the reference's dilation / normal / min_filter kernels (needs oracle/_ref)"""
+    from oracle import build_ref
+    p = core_parameter(130)
+    try:
+        rm = oracle_mod.RefKernelMap(p, "core130")
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not prebuilt and /root/reference absent")
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    W = 130
+    h = rng.standard_normal((W, W)).astype(np.float32)
+    mask = (rng.random((W, W)) < 0.15).astype(np.float32)
+    mask[:, :4] = (rng.random((W, 4)) < 0.6); mask[:, -4:] = (rng.random((W, 4)) < 0.6)   # exercise the row wrap-around
+    ours, _ = oracle_mod.dilation(W, p.dilation_size, h, mask)
+    ref = np.zeros((W, W), np.float32); dummy = np.zeros((W, W), np.float32)
+    _p = oracle_mod._p
+    rm.lib.ref_dilation_filter(C.c_longlong(W * W), _p(h), _p(mask), _p(ref), _p(dummy), C.c_int(0))
+    assert np.array_equal(ours, ref)
+    rm.elevation_map[2] = mask
+    rm.update_normal(ours)
+    # the host build of the reference source has no FMA contraction (g++ -ffp-contract=off) while the oracle
+    # follows nvcc's contraction of CK.py:497 (fma(nx,nx, ny*ny) + 1): last-ulp differences only
+    on = oracle_mod.normal(W, p.resolution, ours, mask)
+    assert np.array_equal(on != 0, rm.normal_map != 0)
+    assert np.abs(on - rm.normal_map).max() <= 2.4e-7
+    # min_filter: the reference updates in place (Gauss-Seidel); with one iteration on a mask whose invalid
+    # cells have no invalid neighbours inside the window the two orders coincide
+    m2 = np.ones((W, W), np.float32); m2[5:-5:4, 5:-5:4] = 0
+    rm.elevation_map[0] = h; rm.elevation_map[2] = m2
+    ref_mf = rm.min_filter(1)
+    ours_mf, _ = oracle_mod.min_filter(W, 1, 1, h, m2)
+    assert np.array_equal(np.nan_to_num(ours_mf), np.nan_to_num(ref_mf))
