@@ -115,15 +115,14 @@ def run_reference_arm(args):
     """Reference arm: the reference's own kernel source (oracle/_ref) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return 0
+        return None
     from elevation_mapping_cupy_b200.parameter import core_parameter
     from oracle import oracle as O
     param = core_parameter(1024)
     try:
         rm = O.RefKernelMap(param, "core1024", parallel=True)
     except Exception as e:       # prebuilt library absent
-        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref not built: {e}"[:200]}))
-        return 0
+        return {"impl": "reference", "unavailable": f"oracle/_ref not built: {e}"[:200]}
     cores = O.lib().oracle_max_threads()
     n_sensors = max(1, args.gpus)
     pools = [make_frames(n_sensors, s, min(N_FRAME_POOL, args.warmup + args.steps)) for s in range(n_sensors)]
@@ -151,11 +150,34 @@ def run_reference_arm(args):
                                        "host by oracle/build_ref.py, OpenMP + CAS atomics; traversability via torch CPU conv"},
             "e2e": {"value": val, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
-    return 0
+    return line
+
+
+class _QuietStdout:
+    """stdout must carry exactly ONE JSON line: park fd 1 on stderr while libraries (NCCL banner, plugin
+    loader prints) are chatty, and give it back for the final print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
+    with _QuietStdout():
+        line = _main()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -294,7 +316,7 @@ def main():
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
-        return 0
+        return None
 
     n_total = world * PTS_PER_SENSOR
     value = n_total / (ms * 1e-3) / 1e6
@@ -341,10 +363,9 @@ def main():
                     "d2h_bytes_per_step": 72, "note": "pinned host cloud -> emap_input_pointcloud (H2D inside), frame stats read back"},
             "gpu_launches": int(launches_per_frame * args.steps), "gpu_launches_per_frame": int(launches_per_frame),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
-    return 0
+    return line
 
 
 if __name__ == "__main__":
