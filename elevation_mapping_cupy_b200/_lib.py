@@ -50,6 +50,8 @@ SIGNATURES = {
     "emap_set_ray_counting": (C.c_int, [C.c_void_p, C.c_int]),
     "emap_shard_begin": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int64,
                                    C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float]),
+    "emap_shard_scratch_bytes": (C.c_int64, [C.c_void_p]),
+    "emap_shard_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "emap_shard_set_overlap_z": (C.c_int, [C.c_void_p, C.c_float]),
     "emap_shard_exchange": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(EmapExchange), C.POINTER(C.c_int32)]),
     "emap_shard_phase": (C.c_int, [C.c_void_p, C.c_int32]),

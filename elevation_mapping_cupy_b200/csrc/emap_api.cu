@@ -62,6 +62,12 @@ struct emap_handle {
   i64 n_points = 0, global_off = 0;
   float pos_noise = 0, ori_noise = 0;
   int phase = 0;              // sharded-frame state machine
+  // multicast-attached scratch (sharded frames over NVLink multicast, emap_shard_attach)
+  bool attached = false;
+  std::vector<const void*> pend_pts;   // device pointers of the frame's clouds (index pass deferred to phase 0)
+  std::vector<int64_t> pend_n;
+  int64_t pend_stride = 0;
+  int pend_dtype = 0, pend_host = 0;
   // export staging
   float* d_export = nullptr;
   // plugin scratch
@@ -189,8 +195,7 @@ template <typename T>
 int launch_index(emap_handle* h, const Pose& q, const T* pts, i64 n, i64 stride, i64 off, int sensor) {
   if (n <= 0) return 0;
   k_index_error<T><<<cdiv(n, 256), 256, 0, h->stream>>>(h->dc, q, pts, n, stride, h->xyzv + off, h->pidx + off, h->map,
-                                                           h->sc.cnt_all, h->sc.cnt_inl, h->fs, h->rays + off,
-                                                           h->ray_ctl + 2 * sensor);
+                                                           h->sc, h->fs, h->rays + off, h->ray_ctl + 2 * sensor);
   LAUNCH_CHECK();
   return 0;
 }
@@ -251,15 +256,23 @@ int frame_begin(emap_handle* h, int32_t n_sensors, const void* const* points, co
     CK(cudaEventRecord(h->copy_done, h->copy_stream));
     CK(cudaStreamWaitEvent(h->stream, h->copy_done, 0));
   }
+  h->pend_pts.assign(dp, dp + n_sensors);
+  h->pend_n.assign(n, n + n_sensors);
+  h->pend_stride = row_stride; h->pend_dtype = dtype; h->pend_host = !is_device_ptr;
+  h->phase = -1;                                                   // index pass pending
+  return 0;
+}
+
+// index + error-count pass of every sensor (CK.py:280-345)
+int frame_index(emap_handle* h) {
+  const int n_sensors = (int)h->pend_pts.size();
   for (int s = 0; s < n_sensors; s++) {
-    rc = dtype == EMAP_F32 ? launch_index<float>(h, h->poses[s], (const float*)dp[s], n[s], row_stride, h->offs[s], s)
-                           : launch_index<double>(h, h->poses[s], (const double*)dp[s], n[s], row_stride, h->offs[s], s);
+    int rc = h->pend_dtype == EMAP_F32
+                 ? launch_index<float>(h, h->poses[s], (const float*)h->pend_pts[s], h->pend_n[s], h->pend_stride, h->offs[s], s)
+                 : launch_index<double>(h, h->poses[s], (const double*)h->pend_pts[s], h->pend_n[s], h->pend_stride, h->offs[s], s);
     if (rc) return rc;
   }
-  if (!is_device_ptr) {
-    CK(cudaEventRecord(h->in_free[h->in_sel ^ 1], h->stream));
-    CK(cudaEventSynchronize(h->copy_done));      // caller may reuse its host buffers on return
-  }
+  if (h->pend_host) CK(cudaEventRecord(h->in_free[h->in_sel ^ 1], h->stream));
   if (stage_mark(h, 1)) return EMAP_ERR_CUDA;
   h->phase = 1;
   return 0;
@@ -281,7 +294,8 @@ int frame_fuse(emap_handle* h) {
 
 int frame_rays(emap_handle* h) {
   if (h->dc.visibility) {
-    k_record<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs);
+    if (h->dc.C % 4 == 0) k_record<4><<<cdiv(h->dc.C / 4, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs);
+    else k_record<1><<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs);
     LAUNCH_CHECK();
     if (stage_mark(h, 4)) return EMAP_ERR_CUDA;
     const size_t sm = sizeof(float) * (size_t)((h->dc.n_steps + 31) & ~31);
@@ -324,7 +338,8 @@ int launch_post(emap_handle* h) {
 }
 
 int frame_finish(emap_handle* h) {
-  k_finalize<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs, h->dc.visibility);
+  if (h->dc.C % 4 == 0) k_finalize<4><<<cdiv(h->dc.C / 4, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs, h->dc.visibility);
+  else k_finalize<1><<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs, h->dc.visibility);
   LAUNCH_CHECK();
   if (stage_mark(h, 6)) return EMAP_ERR_CUDA;
   int rc = launch_post(h);
@@ -459,6 +474,7 @@ int emap_destroy(emap_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  if (h->attached) { h->u32_block = nullptr; h->i64_block = nullptr; h->sc.last = nullptr; h->sc.rec = nullptr; h->sc.ukv = nullptr; h->fs = nullptr; }
   void* ptrs[] = {h->map, h->map_alt, h->normal, h->trav_input, h->u32_block, h->i64_block, h->sc.last, h->sc.rec,
                   h->sc.ukv, h->ukey_x, h->fs, h->steps, h->d_export, h->d_in[0], h->d_in[1], h->xyzv, h->pidx, h->pl[0], h->pl[1],
                   h->pl[2], h->pl[3], h->pl_cnt, h->rays, h->ray_ctl};
@@ -492,11 +508,15 @@ int emap_input_sensors(emap_handle* h, int32_t n_sensors, const void* const* poi
                        int dtype, int is_device_ptr, const float* R, const float* t, float pn, float on) {
   ENTER(h);
   if (!points || !n || !R || !t) return fail(h, EMAP_ERR_INVALID, "emap_input: null argument");
+  if (h->attached) return fail(h, EMAP_ERR_STATE, "handle is attached to a sharded scratch: use the emap_shard_* calls");
   int rc = frame_begin(h, n_sensors, points, n, row_stride, dtype, is_device_ptr, R, t, 0, pn, on);
   if (rc) return rc;
+  if ((rc = frame_index(h))) return rc;
   if ((rc = frame_fuse(h))) return rc;
   if ((rc = frame_rays(h))) return rc;
-  return frame_finish(h);
+  if ((rc = frame_finish(h))) return rc;
+  if (!is_device_ptr) CK(cudaEventSynchronize(h->copy_done));      // caller may reuse its host buffers on return
+  return EMAP_OK;
 }
 
 int emap_input_pointcloud(emap_handle* h, const void* points, int64_t n, int64_t row_stride, int dtype, int is_device_ptr,
@@ -513,12 +533,55 @@ int emap_shard_begin(emap_handle* h, int32_t n_sensors, const void* const* point
                      float on) {
   ENTER(h);
   if (!points || !n || !R || !t) return fail(h, EMAP_ERR_INVALID, "emap_shard_begin: null argument");
-  return frame_begin(h, n_sensors, points, n, row_stride, dtype, is_device_ptr, R, t, global_point_offset, pn, on);
+  int rc = frame_begin(h, n_sensors, points, n, row_stride, dtype, is_device_ptr, R, t, global_point_offset, pn, on);
+  if (rc) return rc;
+  if (!is_device_ptr) CK(cudaEventSynchronize(h->copy_done));      // caller may reuse its host buffers on return
+  // multicast mode: every rank must have reset its frame scalars before anyone pushes -> the caller runs a
+  // cross-rank barrier and then emap_shard_phase(h, 0); NCCL mode: index right away
+  return h->attached ? 0 : frame_index(h);
+}
+
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int64_t emap_shard_scratch_bytes(const emap_handle* h) {
+  if (!h) return EMAP_ERR_INVALID;
+  const size_t C = (size_t)h->dc.C;
+  return (int64_t)(al256(4 * 5 * C) + al256(8 * 3 * C) + al256(8 * C) + al256(8 * C) + al256(4 * C) + al256(sizeof(FrameScalars)));
+}
+
+int emap_shard_attach(emap_handle* h, void* local_base, void* multicast_base, int64_t bytes) {
+  ENTER(h);
+  if (!local_base || !multicast_base || bytes < emap_shard_scratch_bytes(h))
+    return fail(h, EMAP_ERR_INVALID, "emap_shard_attach: need local + multicast base of >= emap_shard_scratch_bytes()");
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t C = (size_t)h->dc.C;
+  char* b = (char*)local_base;
+  FrameScalars keep;
+  CK(cudaMemcpy(&keep, h->fs, sizeof(keep), cudaMemcpyDeviceToHost));
+  // the library's own scratch is released; the symmetric block (owned by the caller) replaces it
+  void* old[] = {h->u32_block, h->i64_block, h->sc.last, h->sc.rec, h->sc.ukv, h->fs};
+  for (void* p : old) if (p && !h->attached) cudaFree(p);
+  h->u32_block = (u32*)b; b += al256(4 * 5 * C);
+  h->i64_block = (i64*)b; b += al256(8 * 3 * C);
+  h->sc.last = (u64*)b; b += al256(8 * C);
+  h->sc.rec = (uint2*)b; b += al256(8 * C);
+  h->sc.ukv = (u32*)b; b += al256(4 * C);
+  h->fs = (FrameScalars*)b;
+  h->sc.cnt_all = h->u32_block; h->sc.cnt_inl = h->u32_block + C; h->sc.cnt_fused = h->u32_block + 2 * C;
+  h->sc.n_out = h->u32_block + 3 * C; h->sc.n_ray = h->u32_block + 4 * C;
+  h->sc.SH = h->i64_block; h->sc.SV = h->i64_block + C; h->sc.DV = h->i64_block + 2 * C;
+  h->sc.mc_off = (i64)((char*)multicast_base - (char*)local_base);
+  CK(cudaMemsetAsync(local_base, 0, (size_t)emap_shard_scratch_bytes(h), h->stream));
+  CK(cudaMemsetAsync(h->sc.ukv, 0xff, sizeof(u32) * C, h->stream));
+  CK(cudaMemcpyAsync(h->fs, &keep, sizeof(keep), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->attached = true;
+  return EMAP_OK;
 }
 
 int emap_shard_set_overlap_z(emap_handle* h, float z_abs) {
   ENTER(h);
-  if (h->phase < 1) return fail(h, EMAP_ERR_STATE, "emap_shard_set_overlap_z must follow emap_shard_begin");
+  if (h->phase != 1 && h->phase != -1) return fail(h, EMAP_ERR_STATE, "emap_shard_set_overlap_z must follow emap_shard_begin");
   k_frame_reset<<<1, 32, 0, h->stream>>>(h->fs, z_abs - h->center[2], 0, nullptr, 0);
   LAUNCH_CHECK();
   return EMAP_OK;
@@ -556,6 +619,10 @@ int emap_shard_exchange(emap_handle* h, int32_t phase, emap_exchange* out, int32
 
 int emap_shard_phase(emap_handle* h, int32_t phase) {
   ENTER(h);
+  if (phase == 0) {
+    if (h->phase != -1) return fail(h, EMAP_ERR_STATE, "phase 0 must follow emap_shard_begin on an attached handle");
+    return frame_index(h);
+  }
   if (phase == 1) {
     if (h->phase != 1) return fail(h, EMAP_ERR_STATE, "phase 1 must follow emap_shard_begin");
     return frame_fuse(h);
@@ -572,7 +639,7 @@ int emap_shard_phase(emap_handle* h, int32_t phase) {
     }
     return frame_finish(h);
   }
-  return fail(h, EMAP_ERR_INVALID, "emap_shard_phase: phase must be 1..3");
+  return fail(h, EMAP_ERR_INVALID, "emap_shard_phase: phase must be 0..3");
 }
 
 // ---- read-backs ------------------------------------------------------------------------------

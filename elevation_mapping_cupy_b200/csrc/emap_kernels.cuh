@@ -30,15 +30,35 @@ struct CellScratch {
   u64* last;       // (global point index << 32 | bits(new_h)) max  -> upper_bound of a hit cell, CK.py:191
   uint2* rec;      // ray record, 8 B: {valid cell ? bits(h') : upper-bound key, flags}
   u32* ukv;        // upper-bound key carved into VALID cells by penetrating rays (UKEY_NONE between frames)
+  i64 mc_off;      // sharded frames: byte offset from a local scratch address to its NVLink MULTICAST alias
+                   // (0 = single GPU).  Non-zero: every accumulation is one multimem.red that the NVSwitch
+                   // applies to the replicas of ALL ranks (this one included) -- scatter and collective fused.
 };
+
+// accumulate into the per-cell scratch: local L2 atomic, or one in-switch multicast reduction
+__device__ __forceinline__ void red_add(u32* p, u32 v, i64 mc) {
+  if (mc) asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"((char*)p + mc), "r"(v) : "memory");
+  else atomicAdd(p, v);
+}
+__device__ __forceinline__ void red_add(u64* p, u64 v, i64 mc) {
+  if (mc) asm volatile("multimem.red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"((char*)p + mc), "l"(v) : "memory");
+  else atomicAdd(p, v);
+}
+__device__ __forceinline__ void red_max(u64* p, u64 v, i64 mc) {
+  if (mc) asm volatile("multimem.red.relaxed.sys.global.max.u64 [%0], %1;" ::"l"((char*)p + mc), "l"(v) : "memory");
+  else atomicMax(p, v);
+}
+__device__ __forceinline__ void red_min(u32* p, u32 v, i64 mc) {
+  if (mc) asm volatile("multimem.red.relaxed.sys.global.min.u32 [%0], %1;" ::"l"((char*)p + mc), "r"(v) : "memory");
+  else atomicMin(p, v);
+}
 
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64 n, const i64 stride,
               float4* __restrict__ xyzv, int* __restrict__ pidx, const float* __restrict__ map,
-              u32* __restrict__ cnt_all, u32* __restrict__ cnt_inl, FrameScalars* fs,
-              Ray* __restrict__ rays, int* __restrict__ ray_ctl) {
+              const CellScratch s, FrameScalars* fs, Ray* __restrict__ rays, int* __restrict__ ray_ctl) {
   const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   i64 e = 0; int ec = 0, nv = 0;
   Ray ray; ray.len = -1.f;
@@ -78,30 +98,19 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
         if (mvalid > 0.5f && (double)fabsf(mh - g.z) < (double)mv * c.mahal
             && (double)mv < c.inlier_var_half && (double)mt > c.trav_inlier) {   // CK.py:328-330
           e = fix32(g.z - mh); ec = 1;
-          atomicAdd(cnt_inl + idx, 1u);
+          red_add(s.cnt_inl + idx, 1u, s.mc_off);
         }
-        atomicAdd(cnt_all + idx, 1u);
+        red_add(s.cnt_all + idx, 1u, s.mc_off);
       }
     }
     xyzv[i] = o; pidx[i] = rec;
   }
-  // compact the rays that have at least one march step (s_0 < len) into the sensor's ray list:
-  // one atomic per warp; the list order is irrelevant (every ray effect is a commutative integer atomic)
-  {
-    const bool has = ray.len > c.first_step;
-    const u32 bal = __ballot_sync(0xffffffffu, has);
-    if (bal) {
-      const int lane = threadIdx.x & 31;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(ray_ctl, __popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (has) {
-        float4* dst = reinterpret_cast<float4*>(rays + base + __popc(bal & ((1u << lane) - 1u)));
-        dst[0] = make_float4(ray.x, ray.y, ray.z, ray.len);
-        dst[1] = make_float4(ray.rx, ray.ry, ray.rz, ray.len_far);
-      }
-    }
-  }
+  // compact the rays that have at least one march step (s_0 < len) into the sensor's ray list: one
+  // atomic per CTA; the list order is irrelevant (every ray effect is a commutative integer atomic)
+  __shared__ int s_rc[9];
+  const bool has_ray = ray.len > c.first_step;
+  const u32 ray_bal = __ballot_sync(0xffffffffu, has_ray);
+  if ((threadIdx.x & 31) == 0) s_rc[threadIdx.x >> 5] = __popc(ray_bal);
   // block reduction -> one integer atomic per block (order independent)
   for (int o = 16; o > 0; o >>= 1) {
     e += __shfl_down_sync(0xffffffffu, e, o);
@@ -114,9 +123,20 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int k = 1; k < 8; k++) { e += s_e[k]; ec += s_c[k]; nv += s_v[k]; }
-    if (e != 0) atomicAdd((u64*)&fs->E, (u64)e);
-    if (ec) atomicAdd((u64*)&fs->ecnt, (u64)ec);
+    if (e != 0) red_add((u64*)&fs->E, (u64)e, s.mc_off);
+    if (ec) red_add((u64*)&fs->ecnt, (u64)ec, s.mc_off);
     if (nv) atomicAdd((u64*)&fs->nvalid, (u64)nv);
+    int tot = 0;
+    for (int k = 0; k < 8; k++) tot += s_rc[k];
+    s_rc[8] = tot ? atomicAdd(ray_ctl, tot) : 0;
+  }
+  __syncthreads();
+  if (has_ray) {
+    int base = s_rc[8];
+    for (int k = 0; k < w; k++) base += s_rc[k];
+    float4* dst = reinterpret_cast<float4*>(rays + base + __popc(ray_bal & ((1u << l) - 1u)));
+    dst[0] = make_float4(ray.x, ray.y, ray.z, ray.len);
+    dst[1] = make_float4(ray.rx, ray.ry, ray.rz, ray.len_far);
   }
 }
 
@@ -160,7 +180,7 @@ k_fuse(const DevCfg c, const i64 n, const i64 global_off, const float4* __restri
   const float mv = __ldg(map + c.C + idx);
   const float num_points = (float)s.cnt_all[idx];                 // CK.py:172
   if ((double)fabsf(mh - z) > (double)mv * c.mahal) {
-    atomicAdd(s.n_out + idx, 1u);                                 // CK.py:174
+    red_add(s.n_out + idx, 1u, s.mc_off);                         // CK.py:174
   } else if (c.edge_sharpen && (double)num_points > c.wall_thresh
              && (double)z < (double)mh - (double)mv * c.mahal / (double)num_points) {
     // CK.py:177-179 edge sharpening: skip
@@ -168,12 +188,24 @@ k_fuse(const DevCfg c, const i64 n, const i64 global_off, const float4* __restri
     const float den = __fadd_rn(mv, v);
     const float new_h = __fdiv_rn(__fmaf_rn(mh, v, __fmul_rn(z, mv)), den);   // CK.py:181 (nvcc contraction)
     const float new_v = __fdiv_rn(__fmul_rn(mv, v), den);                     // CK.py:182
-    atomicAdd((u64*)(s.SH + idx), (u64)fix32(new_h));
-    atomicAdd((u64*)(s.SV + idx), (u64)fix32(new_v));
-    atomicAdd(s.cnt_fused + idx, 1u);
-    atomicMax(s.last + idx, ((u64)(u32)(global_off + i) << 32) | (u64)__float_as_uint(new_h));
+    red_add((u64*)(s.SH + idx), (u64)fix32(new_h), s.mc_off);
+    red_add((u64*)(s.SV + idx), (u64)fix32(new_v), s.mc_off);
+    red_add(s.cnt_fused + idx, 1u, s.mc_off);
+    red_max(s.last + idx, ((u64)(u32)(global_off + i) << 32) | (u64)__float_as_uint(new_h), s.mc_off);
   }
 }
+
+// V consecutive elements (V = 4: one 16-byte access, needs C % 4 == 0; V = 1: any cell_n)
+template <int V, typename T> __device__ __forceinline__ void ldv(const T* p, T (&a)[V]) {
+  if (V == 4) { const uint4 t = *reinterpret_cast<const uint4*>(p); a[0] = ((const T*)&t)[0]; a[1 % V] = ((const T*)&t)[1]; a[2 % V] = ((const T*)&t)[2]; a[3 % V] = ((const T*)&t)[3]; }
+  else { for (int j = 0; j < V; j++) a[j] = p[j]; }
+}
+template <int V, typename T> __device__ __forceinline__ void stv(T* p, const T (&a)[V]) {
+  if (V == 4) { uint4 t; ((T*)&t)[0] = a[0]; ((T*)&t)[1] = a[1 % V]; ((T*)&t)[2] = a[2 % V]; ((T*)&t)[3] = a[3 % V]; *reinterpret_cast<uint4*>(p) = t; }
+  else { for (int j = 0; j < V; j++) p[j] = a[j]; }
+}
+template <int V, typename T> __device__ __forceinline__ bool anyv(const T (&a)[V]) { bool r = false; for (int j = 0; j < V; j++) r |= (a[j] != (T)0); return r; }
+template <int V, typename T> __device__ __forceinline__ bool diffv(const T (&a)[V], const T (&b)[V]) { bool r = false; for (int j = 0; j < V; j++) r |= (a[j] != b[j]); return r; }
 
 // n sequential fp32 additions of the constant c (the atomicAdds of CK.py:174 / CK.py:251)
 __device__ __forceinline__ float add_n_times(float v, float c, u32 n) {
@@ -186,26 +218,49 @@ __device__ __forceinline__ float add_n_times(float v, float c, u32 n) {
 //      = upper-bound key (UKEY_NONE if unbounded) for invalid cells -- rays atomicMin it in place
 //   .y = RF_* flags
 // The variance a ray needs (CK.py:239) is rebuilt on the rare second level from map[1] and n_out.
+// V consecutive cells per thread, every plane read as one vector up front (HBM-bound pass).
+// Also re-zeroes cnt_all / cnt_inl: no later kernel of the frame reads them.
+template <int V>
 __global__ void __launch_bounds__(256)
 k_record(const DevCfg c, const float* __restrict__ map, const CellScratch s, const FrameScalars* __restrict__ fs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c.C) return;
-  float valid = map[2 * c.C + i], time = map[4 * c.C + i];
-  const bool hit = s.cnt_fused[i] > 0;
-  if (hit) { valid = 1.f; time = 0.f; }                                     // CK.py:187-192
-  u32 fl = (time < 0.5f ? RF_T05 : 0u) | (time < 1.0f ? RF_T10 : 0u)
-         | ((double)(float)s.cnt_inl[i] > c.wall_thresh ? RF_WALL : 0u);
-  u32 a;
-  if (valid < 0.5f) {
-    const float isup = map[6 * c.C + i];
-    a = (hit || isup < 0.5f) ? UKEY_NONE : fkey(map[5 * c.C + i]);
-  } else {
-    fl |= RF_VALID;
-    float h = map[i];
-    if (fs->applied) h = __fadd_rn(h, fs->shift);
-    a = __float_as_uint(h);
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+  if (i0 >= c.C) return;
+  const size_t C = (size_t)c.C;
+  float h4[V], va4[V], ti4[V], up4[V], iu4[V];
+  u32 cf4[V], ci4[V], ca4[V];
+  ldv<V>(map + i0, h4); ldv<V>(map + 2 * C + i0, va4); ldv<V>(map + 4 * C + i0, ti4);
+  ldv<V>(map + 5 * C + i0, up4); ldv<V>(map + 6 * C + i0, iu4);
+  ldv<V>(s.cnt_fused + i0, cf4); ldv<V>(s.cnt_inl + i0, ci4); ldv<V>(s.cnt_all + i0, ca4);
+  const int applied = fs->applied; const float shift = fs->shift;
+  u32 oa[V], ofl[V];
+#pragma unroll
+  for (int j = 0; j < V; j++) {
+    float valid = va4[j], time = ti4[j];
+    const bool hit = cf4[j] > 0;
+    if (hit) { valid = 1.f; time = 0.f; }                                    // CK.py:187-192
+    u32 fl = (time < 0.5f ? RF_T05 : 0u) | (time < 1.0f ? RF_T10 : 0u)
+           | ((double)(float)ci4[j] > c.wall_thresh ? RF_WALL : 0u);
+    u32 a;
+    if (valid < 0.5f) {
+      a = (hit || iu4[j] < 0.5f) ? UKEY_NONE : fkey(up4[j]);
+    } else {
+      fl |= RF_VALID;
+      float h = h4[j];
+      if (applied) h = __fadd_rn(h, shift);
+      a = __float_as_uint(h);
+    }
+    oa[j] = a; ofl[j] = fl;
   }
-  s.rec[i] = make_uint2(a, fl);
+  if (V == 4) {
+    uint4* dst = reinterpret_cast<uint4*>(s.rec + i0);
+    dst[0] = make_uint4(oa[0], ofl[0], oa[1 % V], ofl[1 % V]);
+    dst[1] = make_uint4(oa[2 % V], ofl[2 % V], oa[3 % V], ofl[3 % V]);
+  } else {
+    for (int j = 0; j < V; j++) s.rec[i0 + j] = make_uint2(oa[j], ofl[j]);
+  }
+  const u32 zero[V] = {};
+  if (anyv<V>(ca4)) stv<V>(s.cnt_all + i0, zero);
+  if (anyv<V>(ci4)) stv<V>(s.cnt_inl + i0, zero);
 }
 
 // CK.py:198-259 ray-cast half as a persistent kernel.  The rays of the frame were set up and compacted
@@ -269,7 +324,10 @@ k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __res
       const uint2 rc = s.rec[nidx];
       if (!(rc.y & RF_VALID)) {                                   // CK.py:229-235 carve the upper bound
         const u32 key = fkey(nz);
-        if (key < rc.x) atomicMin(&s.rec[nidx].x, key);
+        if (key < rc.x) {
+          if (!s.mc_off) atomicMin(&s.rec[nidx].x, key);          // single GPU: the record itself carries the min
+          else if (key < __ldcg(s.ukv + nidx)) red_min(s.ukv + nidx, key, s.mc_off);   // sharded: min over all ranks
+        }
         continue;
       }
       if (rc.y & RF_T05) continue;                                // CK.py:237
@@ -283,9 +341,9 @@ k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __res
       const float product = __fadd_rn(__fadd_rn(__fmul_rn(rx, n0), __fmul_rn(ry, n1)), __fmul_rn(rz, n2));   // CK.py:103-108
       if ((double)fabsf(product) < c.cos_thresh) continue;        // CK.py:245
       if ((rc.y & RF_WALL) && (rc.y & RF_T10)) continue;          // CK.py:246-247
-      atomicAdd((u64*)(s.DV + nidx), (u64)dec_fix);               // CK.py:250
-      atomicAdd(s.n_ray + nidx, 1u);                              // CK.py:251
-      atomicMin(s.ukv + nidx, fkey(nz));                          // CK.py:253-256
+      red_add((u64*)(s.DV + nidx), (u64)dec_fix, s.mc_off);       // CK.py:250
+      red_add(s.n_ray + nidx, 1u, s.mc_off);                      // CK.py:251
+      red_min(s.ukv + nidx, fkey(nz), s.mc_off);                  // CK.py:253-256
     }
     r = __shfl_sync(0xffffffffu, pend, 0);
   }
@@ -303,65 +361,95 @@ k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __res
 
 // Apply every side effect of the frame to the state planes, then average_map_kernel
 // (CK.py:362-384) and clear_overlap_map (EM.py:393-410); re-zero the consumed scratch.
+template <int V>
 __global__ void __launch_bounds__(256)
 k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const FrameScalars* __restrict__ fs,
            const int rays_ran) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c.C) return;
-  const int C = c.C;
-  const u32 cf = s.cnt_fused[i], no = s.n_out[i], ca = s.cnt_all[i];
-  const u32 nr = rays_ran ? s.n_ray[i] : 0u;
-  const int applied = fs->applied;
-  const int r = i / c.W, col = i - r * c.W;
-  const bool in_win = c.overlap && r >= c.cell_min && r < c.cell_max && col >= c.cell_min && col < c.cell_max;
-  float h0 = map[i], v0 = map[C + i], valid0 = map[2 * C + i];
-  float time0 = map[4 * C + i], upper0 = map[5 * C + i], isup0 = map[6 * C + i];
-  float h = h0, v = v0, valid = valid0, time = time0, upper = upper0, isup = isup0;
-  if (applied) h = __fadd_rn(h, fs->shift);
-  v = add_n_times(v, c.c_out, no);
-  if (cf > 0) {                                                   // CK.py:187-192
-    valid = 1.f; time = 0.f; isup = 0.f;
-    upper = __uint_as_float((u32)(s.last[i] & 0xffffffffull));
-  }
+  // V consecutive cells per thread; the dense planes are read as vectors up front, the sparse
+  // accumulators (sums, keys) only for the cells that were touched.
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+  if (i0 >= c.C) return;
+  const size_t C = (size_t)c.C;
+  float h0[V], v0[V], va0[V], ti0[V], up0[V], iu0[V];
+  ldv<V>(map + i0, h0); ldv<V>(map + C + i0, v0); ldv<V>(map + 2 * C + i0, va0);
+  ldv<V>(map + 4 * C + i0, ti0); ldv<V>(map + 5 * C + i0, up0); ldv<V>(map + 6 * C + i0, iu0);
+  u32 cf4[V], no4[V], nr4[V] = {}, ca4[V] = {}, rk4[V] = {}, kv4[V];
+  ldv<V>(s.cnt_fused + i0, cf4); ldv<V>(s.n_out + i0, no4);
+  for (int j = 0; j < V; j++) kv4[j] = UKEY_NONE;
   if (rays_ran) {
-    const float valid_pf = valid;                                 // validity after the fusion stores
-    const u32 key0 = (isup < 0.5f) ? UKEY_NONE : fkey(upper);
-    if (nr > 0) {
-      valid = __fadd_rn(valid, (float)unfix32(s.DV[i]));          // CK.py:250
-      v = add_n_times(v, c.c_out, nr);                            // CK.py:251
+    ldv<V>(s.n_ray + i0, nr4); ldv<V>(s.ukv + i0, kv4);
+    if (V == 4) {
+      const uint4 R0 = reinterpret_cast<const uint4*>(s.rec + i0)[0], R1 = reinterpret_cast<const uint4*>(s.rec + i0)[1];
+      rk4[0] = R0.x; rk4[1 % V] = R0.z; rk4[2 % V] = R1.x; rk4[3 % V] = R1.z;
+    } else {
+      for (int j = 0; j < V; j++) rk4[j] = s.rec[i0 + j].x;
     }
-    // true min over rays (CK.py:230-233,253-256): invalid cells carry it in rec.x, valid cells in ukv
-    u32 ukey;
-    if (valid_pf < 0.5f) ukey = s.rec[i].x;
-    else { const u32 kv = s.ukv[i]; ukey = min(key0, kv); if (kv != UKEY_NONE) s.ukv[i] = UKEY_NONE; }
-    if (ukey != key0) { upper = funkey(ukey); isup = 1.f; }
+  } else {
+    ldv<V>(s.cnt_all + i0, ca4);                                 // k_record did not run: re-zero the counts here
   }
-  // average_map_kernel CK.py:362-384
-  const float valid_in = valid;
-  if (cf > 0) {
-    const double cnt = (double)cf;
-    const float mean_v = (float)(unfix32(s.SV[i]) / cnt);
-    if ((double)mean_v > c.max_variance) { h = 0.f; v = c.init_var; valid = 0.f; }
-    else { h = (float)(unfix32(s.SH[i]) / cnt); v = mean_v; valid = 1.f; }
+  const int applied = fs->applied;
+  const float shift = fs->shift;
+  float h4[V], v4[V], va4[V], ti4[V], up4[V], iu4[V];
+  const int r = i0 / c.W, col0 = i0 - r * c.W;
+  const float hmin = __fsub_rn(fs->overlap_tz, c.overlap_z_f), hmax = __fadd_rn(fs->overlap_tz, c.overlap_z_f);
+#pragma unroll
+  for (int j = 0; j < V; j++) {
+    const int i = i0 + j;
+    const u32 cf = cf4[j], no = no4[j], nr = nr4[j];
+    float h = h0[j], v = v0[j], valid = va0[j], time = ti0[j], upper = up0[j], isup = iu0[j];
+    if (applied) h = __fadd_rn(h, shift);
+    v = add_n_times(v, c.c_out, no);
+    if (cf > 0) {                                                 // CK.py:187-192
+      valid = 1.f; time = 0.f; isup = 0.f;
+      upper = __uint_as_float((u32)(s.last[i] & 0xffffffffull));
+    }
+    if (rays_ran) {
+      const float valid_pf = valid;                               // validity after the fusion stores
+      const u32 key0 = (isup < 0.5f) ? UKEY_NONE : fkey(upper);
+      if (nr > 0) {
+        valid = __fadd_rn(valid, (float)unfix32(s.DV[i]));        // CK.py:250
+        v = add_n_times(v, c.c_out, nr);                          // CK.py:251
+      }
+      // true min over rays (CK.py:230-233,253-256): invalid cells carry it in rec.x (single GPU) or ukv
+      // (sharded), valid cells in ukv
+      const u32 ukey = min((valid_pf < 0.5f) ? rk4[j] : key0, kv4[j]);
+      if (ukey != key0) { upper = funkey(ukey); isup = 1.f; }
+    }
+    // average_map_kernel CK.py:362-384
+    const float valid_in = valid;
+    if (cf > 0) {
+      const double cnt = (double)cf;
+      const float mean_v = (float)(unfix32(s.SV[i]) / cnt);
+      if ((double)mean_v > c.max_variance) { h = 0.f; v = c.init_var; valid = 0.f; }
+      else { h = (float)(unfix32(s.SH[i]) / cnt); v = mean_v; valid = 1.f; }
+    }
+    if (valid_in < 0.5f) { h = 0.f; v = c.init_var; valid = 0.f; }
+    // clear_overlap_map EM.py:393-410
+    int rr = r, cc = col0 + j;
+    if (cc >= c.W) { cc -= c.W; rr += 1; }
+    if (c.overlap && rr >= c.cell_min && rr < c.cell_max && cc >= c.cell_min && cc < c.cell_max) {
+      if (h < hmin || h > hmax) { h = 0.f; v = c.init_var; valid = 0.f; }
+      if (upper < hmin || upper > hmax) { upper = 0.f; isup = 0.f; }
+    }
+    h4[j] = h; v4[j] = v; va4[j] = valid; ti4[j] = time; up4[j] = upper; iu4[j] = isup;
+    // re-zero the sparse accumulators
+    if (cf) { s.SH[i] = 0; s.SV[i] = 0; s.last[i] = 0; }
+    if (nr) s.DV[i] = 0;
   }
-  if (valid_in < 0.5f) { h = 0.f; v = c.init_var; valid = 0.f; }
-  // clear_overlap_map EM.py:393-410
-  if (in_win) {
-    const float hmin = __fsub_rn(fs->overlap_tz, c.overlap_z_f), hmax = __fadd_rn(fs->overlap_tz, c.overlap_z_f);
-    if (h < hmin || h > hmax) { h = 0.f; v = c.init_var; valid = 0.f; }
-    if (upper < hmin || upper > hmax) { upper = 0.f; isup = 0.f; }
-  }
-  if (h != h0 || applied) map[i] = h;
-  if (v != v0) map[C + i] = v;
-  if (valid != valid0) map[2 * C + i] = valid;
-  if (time != time0) map[4 * C + i] = time;
-  if (upper != upper0) map[5 * C + i] = upper;
-  if (isup != isup0) map[6 * C + i] = isup;
-  // re-zero scratch
-  if (ca) { s.cnt_all[i] = 0; s.cnt_inl[i] = 0; }
-  if (no) s.n_out[i] = 0;
-  if (cf) { s.cnt_fused[i] = 0; s.SH[i] = 0; s.SV[i] = 0; s.last[i] = 0; }
-  if (nr) { s.n_ray[i] = 0; s.DV[i] = 0; }
+  if (applied || diffv<V>(h4, h0)) stv<V>(map + i0, h4);
+  if (diffv<V>(v4, v0)) stv<V>(map + C + i0, v4);
+  if (diffv<V>(va4, va0)) stv<V>(map + 2 * C + i0, va4);
+  if (diffv<V>(ti4, ti0)) stv<V>(map + 4 * C + i0, ti4);
+  if (diffv<V>(up4, up0)) stv<V>(map + 5 * C + i0, up4);
+  if (diffv<V>(iu4, iu0)) stv<V>(map + 6 * C + i0, iu4);
+  const u32 zero[V] = {};
+  if (anyv<V>(cf4)) stv<V>(s.cnt_fused + i0, zero);
+  if (anyv<V>(no4)) stv<V>(s.n_out + i0, zero);
+  if (anyv<V>(nr4)) stv<V>(s.n_ray + i0, zero);
+  if (anyv<V>(ca4)) { stv<V>(s.cnt_all + i0, zero); stv<V>(s.cnt_inl + i0, zero); }
+  bool kvd = false;
+  for (int j = 0; j < V; j++) kvd |= kv4[j] != UKEY_NONE;
+  if (kvd) { u32 none[V]; for (int j = 0; j < V; j++) none[j] = UKEY_NONE; stv<V>(s.ukv + i0, none); }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -60,7 +60,9 @@ def global_point_offsets(local_count, group=None):
 class ShardedElevationMap:
     """Wraps one ElevationMap replica per rank; `input_sensors` is collective over `group`."""
 
-    def __init__(self, elevation_map, group=None, static_offsets=None):
+    def __init__(self, elevation_map, group=None, static_offsets=None, mode="auto"):
+        """mode: "multicast" (NVLink multicast reductions fused into the kernels), "nccl" (three integer
+        all-reduces per frame) or "auto" (multicast when the fabric offers a multicast pointer)."""
         import torch
         self.em = elevation_map
         self.group = group
@@ -72,9 +74,40 @@ class ShardedElevationMap:
         cur = torch.cuda.current_stream()
         self.stream = cur if cur.cuda_stream != 0 else torch.cuda.Stream()
         em._check(em._L.emap_set_stream(em._h, C.c_void_p(self.stream.cuda_stream)))
+        self.side = torch.cuda.Stream()
         self._cache = {}
+        self.mode = "nccl"
+        self._symm = None
+        if mode in ("auto", "multicast"):
+            ok = self._attach_multicast()
+            if not ok and mode == "multicast":
+                raise RuntimeError("NVLink multicast is not available on this fabric")
 
-    def _exchange(self, phase):
+    def _attach_multicast(self):
+        import torch.distributed as dist
+        torch = self.torch
+        em = self.em
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            nbytes = int(em._L.emap_shard_scratch_bytes(em._h))
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=f"cuda:{em.device}")
+            grp = self.group if self.group is not None else dist.group.WORLD
+            hdl = symm_mem.rendezvous(buf, grp.group_name)
+            mc = int(hdl.multicast_ptr)
+        except Exception as e:          # no symmetric-memory support in this build / fabric
+            print(f"[sharded] multicast unavailable ({type(e).__name__}: {e}); using NCCL all-reduces")
+            return False
+        if mc == 0:
+            return False
+        torch.cuda.synchronize()
+        em._check(em._L.emap_shard_attach(em._h, C.c_void_p(buf.data_ptr()), C.c_void_p(mc), nbytes))
+        hdl.barrier()
+        torch.cuda.synchronize()
+        self._symm = (buf, hdl)
+        self.mode = "multicast"
+        return True
+
+    def _plan(self, phase):
         em = self.em
         arr = (_lib.EmapExchange * 4)()
         n = C.c_int32(4)
@@ -88,7 +121,27 @@ class ShardedElevationMap:
                 t = self.torch.as_tensor(_Buf(ptr, count, _TYPESTR[dt], em), device=f"cuda:{em.device}")
                 self._cache[key] = t
             todo.append((t, op))
-        all_reduce_buffers(todo, self.group)
+        return todo
+
+    def _exchange(self, phase):
+        all_reduce_buffers(self._plan(phase), self.group)
+
+    def _exchange2_overlapped(self):
+        """Exchange 2: only the int32 counts (cnt_fused | n_out) gate the ray-cast; the fixed-point sums and the
+        last-writer keys are consumed by the finalise pass, so their all-reduces run on a side stream under the
+        ray-cast.  Returns the pending work handles."""
+        import torch.distributed as dist
+        ops = {"SUM": dist.ReduceOp.SUM, "MAX": dist.ReduceOp.MAX, "MIN": dist.ReduceOp.MIN}
+        todo = self._plan(2)
+        critical = [(t, op) for t, op in todo if t.dtype == self.torch.int32]
+        deferred = [(t, op) for t, op in todo if t.dtype != self.torch.int32]
+        all_reduce_buffers(critical, self.group)
+        self.side.wait_stream(self.stream)
+        works = []
+        with self.torch.cuda.stream(self.side):
+            for t, op in deferred:
+                works.append(dist.all_reduce(t, op=ops[op], group=self.group, async_op=True))
+        return works
 
     def input_sensors(self, clouds, Rs, ts, position_noise, orientation_noise, device_ptrs=False, overlap_z=None):
         """`overlap_z`: absolute z of the frame's first sensor (rank 0's), the same value on every rank."""
@@ -126,9 +179,23 @@ class ShardedElevationMap:
                                      tm.ctypes.data, off, float(position_noise), float(orientation_noise)))
         if overlap_z is not None:
             em._check(L.emap_shard_set_overlap_z(h, float(overlap_z)))
+        if self.mode == "multicast":
+            # every accumulation of the frame kernels is a multimem.red applied to all replicas by the switch;
+            # only stream-ordered cross-rank barriers separate the phases (no NCCL, no host sync)
+            bar = self._symm[1].barrier
+            bar()                                   # all ranks have reset their frame scalars / finished the last frame
+            em._check(L.emap_shard_phase(h, 0)); bar()
+            em._check(L.emap_shard_phase(h, 1)); bar()
+            em._check(L.emap_shard_phase(h, 2)); bar()
+            em._check(L.emap_shard_phase(h, 3))
+            return
         self._exchange(1)
         em._check(L.emap_shard_phase(h, 1))
-        self._exchange(2)
+        works = self._exchange2_overlapped()
         em._check(L.emap_shard_phase(h, 2))
         self._exchange(3)
+        with self.torch.cuda.stream(self.side):
+            for w in works:
+                w.wait()
+        self.stream.wait_stream(self.side)
         em._check(L.emap_shard_phase(h, 3))

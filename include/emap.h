@@ -134,12 +134,20 @@ typedef struct emap_exchange {
 int emap_shard_begin(emap_handle* h, int32_t n_sensors, const void* const* points, const int64_t* n,
                      int64_t row_stride, int dtype, int is_device_ptr, const float* R, const float* t,
                      int64_t global_point_offset, float position_noise, float orientation_noise);
+/* NVLink-multicast mode (replaces the three all-reduces): the caller allocates one symmetric block of
+ * emap_shard_scratch_bytes() per rank (e.g. torch.distributed._symmetric_memory), rendezvouses it and hands
+ * the library its own base and the MULTICAST alias.  From then on every per-cell accumulation of the frame
+ * kernels is a single `multimem.red` that the NVSwitch applies to the replicas of all ranks -- the scatter and
+ * the collective are one instruction.  Frame = emap_shard_begin, barrier, phase 0 (index), barrier, phase 1,
+ * barrier, phase 2, barrier, phase 3; the barriers are the caller's (stream-ordered, cross-rank). */
+int64_t emap_shard_scratch_bytes(const emap_handle* h);
+int emap_shard_attach(emap_handle* h, void* local_base, void* multicast_base, int64_t bytes);
 /* Height reference of clear_overlap_map (EM.py:400-401) for a sharded frame: the absolute z of the
  * FIRST sensor of the whole frame (rank 0's), so that every replica clears the same cells.  Call
  * between emap_shard_begin and phase 3; without it a rank uses its own first sensor. */
 int emap_shard_set_overlap_z(emap_handle* h, float sensor_z_absolute);
 int emap_shard_exchange(emap_handle* h, int32_t phase, emap_exchange* out, int32_t* n_out /*in: capacity*/);
-int emap_shard_phase(emap_handle* h, int32_t phase);   /* 1: fusion, 2: ray-cast, 3: finalise+post */
+int emap_shard_phase(emap_handle* h, int32_t phase);   /* 0: index (attached handles only), 1: fusion, 2: ray-cast, 3: finalise+post */
 
 /* ---- pose / time: EM.py:139-170 move, move_to (WRAP:180-186); EM.py:119-128 clear (WRAP:188-191);
  * EM.py:420-426 update_variance, update_time (WRAP:193-203) ---- */

@@ -32,7 +32,7 @@ def test_point_index_bit_exact_reference_test_shape(oracle_mod):
         assert np.array_equal(inside, oin)
 
 
-@pytest.mark.parametrize("cell_n,frames", [(256, 6), (202, 4)])
+@pytest.mark.parametrize("cell_n,frames", [(256, 6), (202, 4), (131, 3)])
 def test_frames_match_oracle(oracle_mod, cell_n, frames):
     """Config A style: several frames with move_to / update_variance / update_time in between."""
     from elevation_mapping_cupy_b200.parameter import core_parameter

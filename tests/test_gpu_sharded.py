@@ -23,7 +23,8 @@ from elevation_mapping_cupy_b200 import workloads as wl
 from oracle import oracle as O
 p = core_parameter(256)
 em = ElevationMap(p, device=rk)
-sh = ShardedElevationMap(em)
+sh = ShardedElevationMap(em, mode=os.environ.get('EMAP_SHARD_MODE', 'auto'))
+print('mode', sh.mode, flush=True)
 om = O.OracleElevationMap(p, nthreads=0)
 for f in range(3):
     clouds, Rs, ts = [], [], []
@@ -47,7 +48,8 @@ dist.destroy_process_group()
 """
 
 
-def test_two_rank_sharded_frame_matches_oracle(tmp_path):
+@pytest.mark.parametrize("mode", ["nccl", "multicast"])
+def test_two_rank_sharded_frame_matches_oracle(tmp_path, mode):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -55,5 +57,7 @@ def test_two_rank_sharded_frame_matches_oracle(tmp_path):
     script.write_text(_WORKER % {"root": ROOT})
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29544", str(script)],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, EMAP_SHARD_MODE=mode))
+    if mode == "multicast" and "multicast is not available" in (r.stdout + r.stderr):
+        pytest.skip("fabric has no NVLink multicast")
     assert "SHARDED_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
