@@ -197,11 +197,13 @@ k_fuse(const DevCfg c, const i64 n, const i64 global_off, const float4* __restri
 
 // V consecutive elements (V = 4: one 16-byte access, needs C % 4 == 0; V = 1: any cell_n)
 template <int V, typename T> __device__ __forceinline__ void ldv(const T* p, T (&a)[V]) {
-  if (V == 4) { const uint4 t = *reinterpret_cast<const uint4*>(p); a[0] = ((const T*)&t)[0]; a[1 % V] = ((const T*)&t)[1]; a[2 % V] = ((const T*)&t)[2]; a[3 % V] = ((const T*)&t)[3]; }
+  if (V == 2) { const uint2 t = *reinterpret_cast<const uint2*>(p); a[0] = ((const T*)&t)[0]; a[1 % V] = ((const T*)&t)[1]; }
+  else if (V == 4) { const uint4 t = *reinterpret_cast<const uint4*>(p); a[0] = ((const T*)&t)[0]; a[1 % V] = ((const T*)&t)[1]; a[2 % V] = ((const T*)&t)[2]; a[3 % V] = ((const T*)&t)[3]; }
   else { for (int j = 0; j < V; j++) a[j] = p[j]; }
 }
 template <int V, typename T> __device__ __forceinline__ void stv(T* p, const T (&a)[V]) {
-  if (V == 4) { uint4 t; ((T*)&t)[0] = a[0]; ((T*)&t)[1] = a[1 % V]; ((T*)&t)[2] = a[2 % V]; ((T*)&t)[3] = a[3 % V]; *reinterpret_cast<uint4*>(p) = t; }
+  if (V == 2) { uint2 t; ((T*)&t)[0] = a[0]; ((T*)&t)[1] = a[1 % V]; *reinterpret_cast<uint2*>(p) = t; }
+  else if (V == 4) { uint4 t; ((T*)&t)[0] = a[0]; ((T*)&t)[1] = a[1 % V]; ((T*)&t)[2] = a[2 % V]; ((T*)&t)[3] = a[3 % V]; *reinterpret_cast<uint4*>(p) = t; }
   else { for (int j = 0; j < V; j++) p[j] = a[j]; }
 }
 template <int V, typename T> __device__ __forceinline__ bool anyv(const T (&a)[V]) { bool r = false; for (int j = 0; j < V; j++) r |= (a[j] != (T)0); return r; }
@@ -381,6 +383,9 @@ k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const F
     if (V == 4) {
       const uint4 R0 = reinterpret_cast<const uint4*>(s.rec + i0)[0], R1 = reinterpret_cast<const uint4*>(s.rec + i0)[1];
       rk4[0] = R0.x; rk4[1 % V] = R0.z; rk4[2 % V] = R1.x; rk4[3 % V] = R1.z;
+    } else if (V == 2) {
+      const uint4 R0 = reinterpret_cast<const uint4*>(s.rec + i0)[0];
+      rk4[0] = R0.x; rk4[1 % V] = R0.z;
     } else {
       for (int j = 0; j < V; j++) rk4[j] = s.rec[i0 + j].x;
     }

@@ -188,3 +188,58 @@ def test_post_chain_on_random_state(oracle_mod, cell_n, dil):
     compare_state(state, normal, om, label=f"post {cell_n}/{dil}")
     ti = em.traversability_input.cpu().numpy()
     assert np.array_equal(ti, om.traversability_input)
+
+
+def test_config_d_depth_camera_2048_with_plugin_chain(oracle_mod):
+    """BASELINE config D at full size: 2048^2 grid, 1M-point depth-camera cloud with 5 % NaN pixels, then the
+    min_filter -> smooth plugin chain on the result."""
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = core_parameter(2048)
+    em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+    pts, R, t = wl.depth_camera_cloud(3, 0)
+    assert len(pts) == 1000000 and np.isnan(pts).any()
+    for m in (em, om):
+        m.move_to(t, R)
+        m.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+    state, normal = em.get_state()
+    compare_state(state, normal, om, label="config D")
+    idx, valid, inside = em.get_point_record(len(pts))
+    oi, ov, oin = om.last_point_record
+    nan = np.isnan(pts).any(1)
+    assert np.array_equal(idx[~nan], oi[~nan]) and np.array_equal(valid, ov) and np.array_equal(inside, oin)
+    data = np.zeros((p.cell_n - 2, p.cell_n - 2), np.float32)
+    em.get_map_with_name_ref("min_filter", data)
+    mf, _ = oracle_mod.min_filter(p.cell_n, 1, 30, om.elevation_map[0], om.elevation_map[2])
+    ref = np.flip(np.flip((mf + om.center[2])[1:-1, 1:-1], 0), 1)
+    assert np.array_equal(np.isnan(data), np.isnan(ref))
+    assert np.array_equal(np.nan_to_num(data), np.nan_to_num(ref))
+    em.get_map_with_name_ref("smooth", data)
+    assert np.isfinite(data).any()
+
+
+def test_config_e_independent_replicas(oracle_mod):
+    """BASELINE config E in miniature: independent 512^2 maps, one handle (own stream) each, frames issued
+    round-robin without synchronising in between; every replica must equal its own oracle."""
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = core_parameter(512)
+    n_maps = 6
+    ems = [_mk(p) for _ in range(n_maps)]
+    clouds = [[wl.lidar_cloud(4, f, n_rings=32, n_az=3125, max_range=12.0, sensor=0, n_sensors=1) for f in range(2)]
+              for _ in range(n_maps)]
+    for m in range(n_maps):       # a different seed offset per map (SURVEY 8(d) E)
+        clouds[m] = [wl.lidar_cloud(4, 10 * m + f, n_rings=32, n_az=3125, max_range=12.0) for f in range(2)]
+    for f in range(2):
+        for m in range(n_maps):
+            pts, R, t = clouds[m][f]
+            ems[m].move_to(t, R)
+            ems[m].input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+            ems[m].update_time()
+    for m in (0, n_maps - 1):
+        om = oracle_mod.OracleElevationMap(p, nthreads=0)
+        for f in range(2):
+            pts, R, t = clouds[m][f]
+            om.move_to(t, R); om.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02); om.update_time()
+        state, normal = ems[m].get_state()
+        compare_state(state, normal, om, label=f"replica {m}")
