@@ -52,8 +52,11 @@ struct emap_handle {
   float4* xyzv = nullptr;
   int* pidx = nullptr;
   Ray* rays = nullptr;        // compacted rays of the frame, one segment per sensor (at the sensor's point offset)
-  int* ray_ctl = nullptr;     // per sensor: {ray count, work counter}
-  int ray_ctl_cap = 0;        // sensors
+  int* ray_ctl = nullptr;     // per sensor: {ray count, work counter}; two halves used by alternate frames
+  int ray_ctl_cap = 0;        // sensors per half
+  int ray_sel = 0;            // half used by the current frame
+  bool overlap_override = false;
+  float overlap_z_override = 0.f;
   i64 pt_cap = 0;
   int n_sm = 148, rc_blocks_per_sm = 8;
   // last frame description
@@ -195,7 +198,7 @@ template <typename T>
 int launch_index(emap_handle* h, const Pose& q, const T* pts, i64 n, i64 stride, i64 off, int sensor) {
   if (n <= 0) return 0;
   k_index_error<T><<<cdiv(n, 256), 256, 0, h->stream>>>(h->dc, q, pts, n, stride, h->xyzv + off, h->pidx + off, h->map,
-                                                           h->sc, h->fs, h->rays + off, h->ray_ctl + 2 * sensor);
+                                                           h->sc, h->fs, h->rays + off, h->ray_ctl + 2 * (h->ray_sel * h->ray_ctl_cap + sensor));
   LAUNCH_CHECK();
   return 0;
 }
@@ -227,11 +230,12 @@ int frame_begin(emap_handle* h, int32_t n_sensors, const void* const* points, co
     CK(cudaStreamSynchronize(h->stream));
     if (h->ray_ctl) cudaFree(h->ray_ctl);
     h->ray_ctl = nullptr; h->ray_ctl_cap = 0;
-    CK(cudaMalloc(&h->ray_ctl, sizeof(int) * 2 * (n_sensors + 8)));
+    CK(cudaMalloc(&h->ray_ctl, sizeof(int) * 4 * (n_sensors + 8)));
+    CK(cudaMemset(h->ray_ctl, 0, sizeof(int) * 4 * (n_sensors + 8)));
     h->ray_ctl_cap = n_sensors + 8;
   }
-  k_frame_reset<<<1, 32, 0, h->stream>>>(h->fs, h->poses[0].t[2], 1, h->ray_ctl, 2 * n_sensors);
-  LAUNCH_CHECK();
+  h->ray_sel ^= 1;                                 // this half was zeroed by the previous frame's k_drift
+  h->overlap_override = false;
   if (stage_mark(h, 0)) return EMAP_ERR_CUDA;
   const void* dev_pts[64];
   std::vector<const void*> dev_vec;
@@ -279,7 +283,9 @@ int frame_index(emap_handle* h) {
 }
 
 int frame_fuse(emap_handle* h) {
-  k_drift<<<1, 32, 0, h->stream>>>(h->dc, h->fs, h->pos_noise, h->ori_noise);
+  k_drift<<<1, 32, 0, h->stream>>>(h->dc, h->fs, h->pos_noise, h->ori_noise,
+                                   h->overlap_override ? h->overlap_z_override : h->poses[0].t[2], 1,
+                                   h->ray_ctl + 2 * ((h->ray_sel ^ 1) * h->ray_ctl_cap), 2 * h->ray_ctl_cap);
   LAUNCH_CHECK();
   if (stage_mark(h, 2)) return EMAP_ERR_CUDA;
   if (h->n_points > 0) {
@@ -305,10 +311,10 @@ int frame_rays(emap_handle* h) {
       // persistent grid: enough CTAs to fill every SM, never more than one warp per possible ray
       const int grid = (int)std::min<i64>((i64)h->n_sm * h->rc_blocks_per_sm, (n + 3) / 4);
       if (h->count_rays)
-        k_raycast<true><<<grid, RC_THREADS, sm, h->stream>>>(h->dc, h->poses[s], h->rays + h->offs[s], h->ray_ctl + 2 * s,
+        k_raycast<true><<<grid, RC_THREADS, sm, h->stream>>>(h->dc, h->poses[s], h->rays + h->offs[s], h->ray_ctl + 2 * (h->ray_sel * h->ray_ctl_cap + (int)s),
                                                                h->map, h->normal, h->sc, h->steps, h->fs);
       else
-        k_raycast<false><<<grid, RC_THREADS, sm, h->stream>>>(h->dc, h->poses[s], h->rays + h->offs[s], h->ray_ctl + 2 * s,
+        k_raycast<false><<<grid, RC_THREADS, sm, h->stream>>>(h->dc, h->poses[s], h->rays + h->offs[s], h->ray_ctl + 2 * (h->ray_sel * h->ray_ctl_cap + (int)s),
                                                                 h->map, h->normal, h->sc, h->steps, h->fs);
       LAUNCH_CHECK();
     }
@@ -584,8 +590,7 @@ int emap_shard_attach(emap_handle* h, void* local_base, void* multicast_base, in
 int emap_shard_set_overlap_z(emap_handle* h, float z_abs) {
   ENTER(h);
   if (h->phase != 1 && h->phase != -1) return fail(h, EMAP_ERR_STATE, "emap_shard_set_overlap_z must follow emap_shard_begin");
-  k_frame_reset<<<1, 32, 0, h->stream>>>(h->fs, z_abs - h->center[2], 0, nullptr, 0);
-  LAUNCH_CHECK();
+  h->overlap_override = true; h->overlap_z_override = z_abs - h->center[2];     // consumed by k_drift (phase 1)
   return EMAP_OK;
 }
 
@@ -667,8 +672,8 @@ int emap_get_frame_stats(emap_handle* h, emap_frame_stats* out) {
   CK(cudaMemcpyAsync(&f, h->fs, sizeof(f), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   out->mean_error = f.mean_error; out->additive_mean_error = f.additive_mean_error; out->shift_applied = f.shift;
-  out->error_sum = f.error_sum; out->error_cnt = f.ecnt; out->drift_applied = f.applied; out->drift_evaluated = f.evaluated;
-  out->n_points = h->n_points; out->n_valid_points = f.nvalid; out->ray_steps = f.ray_steps; out->ray_visits = f.ray_visits;
+  out->error_sum = f.error_sum; out->error_cnt = f.ecnt_last; out->drift_applied = f.applied; out->drift_evaluated = f.evaluated;
+  out->n_points = h->n_points; out->n_valid_points = f.nvalid_last; out->ray_steps = f.ray_steps; out->ray_visits = f.ray_visits;
   return EMAP_OK;
 }
 

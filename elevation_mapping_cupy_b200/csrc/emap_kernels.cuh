@@ -140,19 +140,26 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
   }
 }
 
-// start of a frame: zero the accumulators (keep mean / additive error), set the overlap-clear reference
-__global__ void k_frame_reset(FrameScalars* fs, float overlap_tz, int zero, int* ray_ctl, int n_ctl) {
-  if (zero) for (int k = threadIdx.x; k < n_ctl; k += blockDim.x) ray_ctl[k] = 0;
-  if (threadIdx.x || blockIdx.x) return;
-  if (zero) { fs->E = 0; fs->ecnt = 0; fs->nvalid = 0; fs->ray_steps = 0; fs->ray_visits = 0; }
-  fs->overlap_tz = overlap_tz;
+// overlap-clear reference of a sharded frame (emap_shard_set_overlap_z)
+__global__ void k_set_overlap(FrameScalars* fs, float overlap_tz) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) fs->overlap_tz = overlap_tz;
 }
 
 // EM.py:346-357
-__global__ void k_drift(const DevCfg c, FrameScalars* fs, float position_noise, float orientation_noise) {
+// Also the frame's housekeeping, so that no separate reset launch is needed: the drift accumulators are
+// consumed here and zeroed for the NEXT frame, the ray-march counters of the previous frame are cleared, the
+// overlap-clear reference is set, and the other half of the double-buffered ray work counters is zeroed.
+__global__ void k_drift(const DevCfg c, FrameScalars* fs, float position_noise, float orientation_noise,
+                        float overlap_tz, int set_overlap, int* ray_ctl_next, int n_ctl) {
+  for (int k = threadIdx.x; k < n_ctl; k += blockDim.x) ray_ctl_next[k] = 0;
   if (threadIdx.x || blockIdx.x) return;
   const i64 ecnt = fs->ecnt;
   const float error_sum = (float)unfix32(fs->E);
+  fs->E = 0; fs->ecnt = 0;
+  fs->nvalid_last = fs->nvalid; fs->nvalid = 0;
+  fs->ray_steps = 0; fs->ray_visits = 0;
+  fs->ecnt_last = ecnt;
+  if (set_overlap) fs->overlap_tz = overlap_tz;
   fs->error_sum = error_sum; fs->shift = 0.f; fs->applied = 0; fs->evaluated = 0;
   if (c.drift_en && (double)(float)ecnt > c.min_drift_cnt
       && ((double)position_noise > c.pos_thresh || (double)orientation_noise > c.ori_thresh)) {
@@ -466,29 +473,6 @@ k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const F
 #define PT_X 32
 #define PT_Y 16
 
-// exact flat-index semantics of CK.py:403-418,429-438 for one cell, from global memory: the neighbour
-// offset (dx,dy) is applied to the FLAT index, so a window that leaves the row on the left / right
-// continues in the previous / next row.  Only cells within K-2 columns of the left or right edge can
-// select such a wrapped neighbour (the wrapped column must itself be inside), so only they come here.
-__device__ float dilate_cell_global(const DevCfg& c, const float* __restrict__ up, const float* __restrict__ valid,
-                                    const float* __restrict__ isup, int r, int cc) {
-  const int W = c.W, k = c.dilation, i = r * W + cc;
-  const float h = up[i];
-  if (__fadd_rn(valid[i], isup[i]) >= 0.5f) return h;
-  float distance = 100.f, near_value = 0.f;
-  for (int dy = -k; dy <= k; dy++)
-    for (int dx = -k; dx <= k; dx++) {
-      int rr = r + dy, c2 = cc + dx;
-      if (c2 < 0) { c2 += W; rr -= 1; } else if (c2 >= W) { c2 -= W; rr += 1; }   // idx / W, idx % W of CK.py:409-410
-      if (rr <= 0 || rr >= W - 1 || c2 <= 0 || c2 >= W - 1) continue;
-      const int idx = rr * W + c2;
-      if (__fadd_rn(valid[idx], isup[idx]) > 0.5f && (float)(dx + dy) < distance) {
-        distance = (float)(dx + dy); near_value = up[idx];
-      }
-    }
-  return distance < 100.f ? near_value : h;
-}
-
 // K = dilation_size as a compile-time constant (0 = use c.dilation at run time).
 template <int KT>
 __global__ void __launch_bounds__(256)
@@ -562,11 +546,42 @@ k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, 
             out = s_up[(sa + dyw) * B + sb + (sp - (dyw + K) - K)];
           }
         }
-      } else {
-        out = dilate_cell_global(c, up, valid, isup, r, cc);
       }
+      // else: one of the K-1 outermost columns -> filled below, one warp per cell
     }
     s_dil[e] = out;
+  }
+  // Border columns (cc <= K-2 or cc >= W-K+1): the flat-index window of CK.py:403-407 wraps into the adjacent
+  // row there.  Rare (2(K-1) columns of the map), so: one WARP per cell, lanes over the (2K+1)^2 candidates,
+  // priority key = (dx+dy, dy) as in the scan of CK.py:429-438, warp-min picks the winner.
+  if (K >= 2 && (c0 - 3 < K - 1 || c0 + PT_X + 3 > W - K)) {
+    const int lane = tid & 31, warp = tid >> 5, side = 2 * K + 1;
+    for (int e = warp; e < DA * DB; e += 8) {
+      const int a = e / DB, b = e - a * DB;
+      const int r = r0 - 3 + a, cc = c0 - 3 + b;
+      if (r < 0 || r >= W || cc < 0 || cc >= W || (cc >= K - 1 && cc <= W - K)) continue;    // warp-uniform
+      const int i = r * W + cc;
+      float out = up[i];
+      if (__fadd_rn(valid[i], isup[i]) < 0.5f) {
+        u32 best = 0xffffffffu;
+        for (int cand = lane; cand < side * side; cand += 32) {
+          const int dy = cand / side - K, dx = cand - (dy + K) * side - K;
+          int rr = r + dy, c2 = cc + dx;
+          if (c2 < 0) { c2 += W; rr -= 1; } else if (c2 >= W) { c2 -= W; rr += 1; }   // idx / W, idx % W of CK.py:409-410
+          if (rr <= 0 || rr >= W - 1 || c2 <= 0 || c2 >= W - 1) continue;
+          const int idx = rr * W + c2;
+          if (__fadd_rn(valid[idx], isup[idx]) > 0.5f) best = min(best, (u32)((dx + dy + 2 * K) << 8 | (dy + K)));
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (best != 0xffffffffu) {
+          const int dy = (int)(best & 255u) - K, dx = (int)(best >> 8) - 2 * K - dy;
+          int rr = r + dy, c2 = cc + dx;
+          if (c2 < 0) { c2 += W; rr -= 1; } else if (c2 >= W) { c2 -= W; rr += 1; }
+          out = up[rr * W + c2];
+        }
+      }
+      if (lane == 0) s_dil[e] = out;
+    }
   }
   __syncthreads();
 #pragma unroll
