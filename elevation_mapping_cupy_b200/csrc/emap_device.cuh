@@ -29,6 +29,8 @@ enum { L_H = 0, L_V = 1, L_VALID = 2, L_TRAV = 3, L_TIME = 4, L_UPPER = 5, L_ISU
 #define RF_T05 2u         // time < 0.5
 #define RF_T10 4u         // time < 1.0
 #define RF_WALL 8u        // inlier count > wall_num_thresh (newmap[3], CK.py:246-247)
+// Border-ring cells (CK.py:34-44,211: rays never act on them) are recorded as RF_VALID|RF_T05, the combination
+// a ray skips without any effect, so the march needs no separate is_inside test.
 
 #define UKEY_NONE 0xffffffffu
 
@@ -106,17 +108,20 @@ __device__ __forceinline__ int axis_cell(const DevCfg& c, float c16) {
   return min(max(i, 0), c.W - 1);                // fp16 clamp is exact for W-1 <= 2048
 }
 
-// both axes with ONE rare branch for the exact path
-__device__ __forceinline__ void axis_cell2(const DevCfg& c, float x16, float y16, int& ix, int& iy) {
-  const float qx = fminf(fmaxf(fmaf(x16, c.inv_res_f, c.half_w_f), -0.5f), c.w_plus_half_f);
-  const float qy = fminf(fmaxf(fmaf(y16, c.inv_res_f, c.half_w_f), -0.5f), c.w_plus_half_f);
+// Both axes with ONE rare branch for the exact path and no integer clamp on the fast path: q is clamped
+// to [0.25, W-0.75] first.  Every true quotient below 1 truncates/clamps to cell 0 and every one >= W-1 to
+// cell W-1, which is what floor of the clamped value gives; values within 1e-3 of an integer (also 1 and
+// W-1 themselves) still go to the double expression.
+__device__ __forceinline__ void axis_cell2(float inv_res, float half_w, float q_hi, const DevCfg& c, float x16, float y16,
+                                           int& ix, int& iy) {
+  const float qx = fminf(fmaxf(fmaf(x16, inv_res, half_w), 0.25f), q_hi);
+  const float qy = fminf(fmaxf(fmaf(y16, inv_res, half_w), 0.25f), q_hi);
   const float fx = floorf(qx), fy = floorf(qy);
   ix = (int)fx; iy = (int)fy;
   if (fmaxf(fabsf((qx - fx) - 0.5f), fabsf((qy - fy) - 0.5f)) > 0.499f) {
-    ix = __double2int_rz((double)x16 / c.resolution + c.half_w);
-    iy = __double2int_rz((double)y16 / c.resolution + c.half_w);
+    ix = min(max(__double2int_rz((double)x16 / c.resolution + c.half_w), 0), c.W - 1);
+    iy = min(max(__double2int_rz((double)y16 / c.resolution + c.half_w), 0), c.W - 1);
   }
-  ix = min(max(ix, 0), c.W - 1); iy = min(max(iy, 0), c.W - 1);
 }
 
 // CK.py:34-44

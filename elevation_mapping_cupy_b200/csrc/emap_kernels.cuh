@@ -258,6 +258,10 @@ k_record(const DevCfg c, const float* __restrict__ map, const CellScratch s, con
       if (applied) h = __fadd_rn(h, shift);
       a = __float_as_uint(h);
     }
+    {   // border ring: make every ray skip the cell (see RF_* in emap_device.cuh); .x stays the cell's own key
+      const int i = i0 + j, rr = i / c.W, cc = i - rr * c.W;
+      if (rr == 0 || rr == c.W - 1 || cc == 0 || cc == c.W - 1) fl = RF_VALID | RF_T05 | RF_T10;
+    }
     oa[j] = a; ofl[j] = fl;
   }
   if (V == 4) {
@@ -293,6 +297,8 @@ k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __res
   int* next = ray_ctl + 1;
   const int W = c.W, C = c.C;
   const float tx = q.t[0], ty = q.t[1], tz = q.t[2];
+  const float inv_res = c.inv_res_f, half_w = c.half_w_f, q_hi = (float)c.W - 0.75f;
+  const u32 s_lane = (u32)__cvta_generic_to_shared(s_steps) + 4u * lane;     // shared-space address of s_steps[lane]
   int n_steps_done = 0, n_visits = 0;
   int pend = 0;
   if (lane == 0) pend = atomicAdd(next, 1);
@@ -306,20 +312,20 @@ k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __res
     const float len_far = rb.w;
     int carry = -1;
     for (int kb = 0; kb < n_pad; kb += 32) {
-      const float sk = s_steps[kb + lane];
+      float sk;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sk) : "r"(s_lane + 4u * kb));
       const bool act = sk < len;
       if (!__any_sync(0xffffffffu, act)) break;
       const float nx = __fmaf_rn(rx, sk, tx);                     // t + ray*s: product exact (CK.py:205-207)
       const float ny = __fmaf_rn(ry, sk, ty);
       int ix, iy;
-      axis_cell2(c, h16(nx), h16(ny), ix, iy);
+      axis_cell2(inv_res, half_w, q_hi, c, h16(nx), h16(ny), ix, iy);
       const int nidx = act ? ix * W + iy : -2;
       int prev = __shfl_up_sync(0xffffffffu, nidx, 1);
       if (lane == 0) prev = carry;
       carry = __shfl_sync(0xffffffffu, nidx, 31);
       if (COUNT) n_steps_done += act;
-      if (nidx == prev || !act) continue;                         // CK.py:209
-      if (!cell_inside(W, ix, iy)) continue;                      // CK.py:211
+      if (nidx == prev || !act) continue;                         // CK.py:209 (CK.py:211: border cells are skipped via their record flags)
       const float nz = __fmaf_rn(rz, sk, tz);
       // CK.py:225-226 `d < 0.1` (d = fp16 of the squared distance to the end point) cannot fire for
       // s < len_far (bound derived where the ray is set up, k_index_error).
