@@ -325,9 +325,9 @@ int frame_rays(emap_handle* h) {
 }
 
 size_t post_smem(const DevCfg& d) {
-  const int HL = d.dilation + 3;
-  return sizeof(float) * (size_t)(2 * (PT_Y + 2 * HL) * (PT_X + 2 * HL) + (PT_Y + 6) * (PT_X + 6) + 2)
-         + sizeof(unsigned long long) * (size_t)(PT_Y + 2 * HL);
+  const int HL = d.dilation + 3, HLX = (HL + 3) & ~3;
+  return sizeof(float) * (size_t)(3 * (PT_Y + 2 * HL) * (PT_X + 2 * HLX) + (PT_Y + 6) * (PT_X + 6) + 2)
+         + sizeof(unsigned long long) * (size_t)(PT_Y + 2 * HL + 2);
 }
 
 int launch_post(emap_handle* h) {

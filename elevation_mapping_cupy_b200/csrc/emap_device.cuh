@@ -116,8 +116,11 @@ __device__ __forceinline__ void axis_cell2(float inv_res, float half_w, float q_
                                            int& ix, int& iy) {
   const float qx = fminf(fmaxf(fmaf(x16, inv_res, half_w), 0.25f), q_hi);
   const float qy = fminf(fmaxf(fmaf(y16, inv_res, half_w), 0.25f), q_hi);
-  const float fx = floorf(qx), fy = floorf(qy);
-  ix = (int)fx; iy = (int)fy;
+  // floor without the conversion unit: q + 2^23 rounded toward -inf is exactly floor(q) + 2^23 for 0 <= q < 2^22,
+  // and its low mantissa bits are the integer.
+  const float rx = __fadd_rd(qx, 8388608.0f), ry = __fadd_rd(qy, 8388608.0f);
+  const float fx = rx - 8388608.0f, fy = ry - 8388608.0f;
+  ix = __float_as_int(rx) - 0x4b000000; iy = __float_as_int(ry) - 0x4b000000;
   if (fmaxf(fabsf((qx - fx) - 0.5f), fabsf((qy - fy) - 0.5f)) > 0.499f) {
     ix = min(max(__double2int_rz((double)x16 / c.resolution + c.half_w), 0), c.W - 1);
     iy = min(max(__double2int_rz((double)y16 / c.resolution + c.half_w), 0), c.W - 1);

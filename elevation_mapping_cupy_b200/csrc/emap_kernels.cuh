@@ -53,6 +53,33 @@ __device__ __forceinline__ void red_min(u32* p, u32 v, i64 mc) {
   else atomicMin(p, v);
 }
 
+// ---- warp aggregation of pushes over RUNS of adjacent lanes that hit the same cell (scan-ordered
+// clouds put consecutive points in the same cell).  Every accumulation is an integer sum / max, so
+// pre-reducing a run in registers and pushing once is exactly equivalent; it is what keeps the number of
+// NVLink multicast reductions per frame (one per update, applied by the switch to every replica) down.
+struct RunInfo { u32 run_mask; bool tail; };
+__device__ __forceinline__ RunInfo run_of(int key, int lane) {
+  const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const u32 heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+  const u32 below = heads & ((2u << lane) - 1u);                     // heads at or below this lane
+  const int start = 31 - __clz(below);
+  const u32 above = heads & ~((2u << lane) - 1u);                    // heads above this lane
+  const int end = above ? (__ffs(above) - 1) : 32;                   // one past the run
+  RunInfo r;
+  r.run_mask = (end == 32 ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << start) - 1u);
+  r.tail = lane == end - 1;
+  return r;
+}
+// inclusive sum of v over the lanes of the run that are at or below this lane (the tail lane gets the run total)
+__device__ __forceinline__ i64 run_sum(i64 v, int lane, u32 run_mask) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const i64 o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d && ((run_mask >> (lane - d)) & 1u)) v += o;
+  }
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -62,6 +89,8 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
   const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   i64 e = 0; int ec = 0, nv = 0;
   Ray ray; ray.len = -1.f;
+  int cell_key = -1 - (int)(threadIdx.x & 31);                    // cell receiving this point's count (unique negative: none)
+  bool is_inl = false;
   if (i < n) {
     const T* p = pts + i * stride;
     float px = (float)p[0], py = (float)p[1], pz = (float)p[2];   // EM.py:456 cast to fp32
@@ -98,12 +127,23 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
         if (mvalid > 0.5f && (double)fabsf(mh - g.z) < (double)mv * c.mahal
             && (double)mv < c.inlier_var_half && (double)mt > c.trav_inlier) {   // CK.py:328-330
           e = fix32(g.z - mh); ec = 1;
-          red_add(s.cnt_inl + idx, 1u, s.mc_off);
+          is_inl = true;
+          if (!s.mc_off) atomicAdd(s.cnt_inl + idx, 1u);
         }
-        red_add(s.cnt_all + idx, 1u, s.mc_off);
+        cell_key = idx;
+        if (!s.mc_off) atomicAdd(s.cnt_all + idx, 1u);
       }
     }
     xyzv[i] = o; pidx[i] = rec;
+  }
+  if (s.mc_off) {   // sharded frame: one multicast reduction per run of lanes in the same cell
+    const int lane = threadIdx.x & 31;
+    const RunInfo ri = run_of(cell_key, lane);
+    const u32 inl = __ballot_sync(0xffffffffu, is_inl) & ri.run_mask;
+    if (ri.tail && cell_key >= 0) {
+      red_add(s.cnt_all + cell_key, (u32)__popc(ri.run_mask), s.mc_off);
+      if (inl) red_add(s.cnt_inl + cell_key, (u32)__popc(inl), s.mc_off);
+    }
   }
   // compact the rays that have at least one march step (s_0 < len) into the sensor's ray list: one
   // atomic per CTA; the list order is irrelevant (every ray effect is a commutative integer atomic)
@@ -176,29 +216,59 @@ k_fuse(const DevCfg c, const i64 n, const i64 global_off, const float4* __restri
        const int* __restrict__ pidx, const float* __restrict__ map, const CellScratch s,
        const FrameScalars* __restrict__ fs) {
   const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int rec = pidx[i];
-  if ((rec & (PT_VALID | PT_INSIDE | PT_SKIP)) != (PT_VALID | PT_INSIDE)) return;
-  const int idx = rec & PT_IDX_MASK;
-  const float4 g = xyzv[i];
-  const float z = g.z, v = g.w;
-  float mh = __ldg(map + idx);
-  if (fs->applied) mh = __fadd_rn(mh, fs->shift);                 // EM.py:357 applied lazily
-  const float mv = __ldg(map + c.C + idx);
-  const float num_points = (float)s.cnt_all[idx];                 // CK.py:172
-  if ((double)fabsf(mh - z) > (double)mv * c.mahal) {
-    red_add(s.n_out + idx, 1u, s.mc_off);                         // CK.py:174
-  } else if (c.edge_sharpen && (double)num_points > c.wall_thresh
-             && (double)z < (double)mh - (double)mv * c.mahal / (double)num_points) {
-    // CK.py:177-179 edge sharpening: skip
-  } else {
-    const float den = __fadd_rn(mv, v);
-    const float new_h = __fdiv_rn(__fmaf_rn(mh, v, __fmul_rn(z, mv)), den);   // CK.py:181 (nvcc contraction)
-    const float new_v = __fdiv_rn(__fmul_rn(mv, v), den);                     // CK.py:182
-    red_add((u64*)(s.SH + idx), (u64)fix32(new_h), s.mc_off);
-    red_add((u64*)(s.SV + idx), (u64)fix32(new_v), s.mc_off);
-    red_add(s.cnt_fused + idx, 1u, s.mc_off);
-    red_max(s.last + idx, ((u64)(u32)(global_off + i) << 32) | (u64)__float_as_uint(new_h), s.mc_off);
+  const int lane = threadIdx.x & 31;
+  int idx = -1 - lane;                    // unique negative key: this lane pushes nothing
+  bool is_out = false, is_fused = false;
+  i64 fh = 0, fv = 0;
+  u64 key = 0;
+  if (i < n) {
+    const int rec = pidx[i];
+    if ((rec & (PT_VALID | PT_INSIDE | PT_SKIP)) == (PT_VALID | PT_INSIDE)) {
+      idx = rec & PT_IDX_MASK;
+      const float4 g = xyzv[i];
+      const float z = g.z, v = g.w;
+      float mh = __ldg(map + idx);
+      if (fs->applied) mh = __fadd_rn(mh, fs->shift);             // EM.py:357 applied lazily
+      const float mv = __ldg(map + c.C + idx);
+      const float num_points = (float)s.cnt_all[idx];             // CK.py:172
+      if ((double)fabsf(mh - z) > (double)mv * c.mahal) {
+        is_out = true;                                            // CK.py:174
+      } else if (c.edge_sharpen && (double)num_points > c.wall_thresh
+                 && (double)z < (double)mh - (double)mv * c.mahal / (double)num_points) {
+        // CK.py:177-179 edge sharpening: skip
+      } else {
+        const float den = __fadd_rn(mv, v);
+        const float new_h = __fdiv_rn(__fmaf_rn(mh, v, __fmul_rn(z, mv)), den);   // CK.py:181 (nvcc contraction)
+        const float new_v = __fdiv_rn(__fmul_rn(mv, v), den);                     // CK.py:182
+        is_fused = true; fh = fix32(new_h); fv = fix32(new_v);
+        key = ((u64)(u32)(global_off + i) << 32) | (u64)__float_as_uint(new_h);   // CK.py:191: last writer in input order
+      }
+    }
+  }
+  if (!s.mc_off) {                        // single GPU: plain L2 atomics
+    if (is_out) atomicAdd(s.n_out + idx, 1u);
+    if (is_fused) {
+      atomicAdd((u64*)(s.SH + idx), (u64)fh);
+      atomicAdd((u64*)(s.SV + idx), (u64)fv);
+      atomicAdd(s.cnt_fused + idx, 1u);
+      atomicMax(s.last + idx, key);
+    }
+    return;
+  }
+  // sharded frame: pre-reduce each run of lanes in the same cell, one multicast reduction per quantity
+  const RunInfo ri = run_of(idx, lane);
+  const u32 outs = __ballot_sync(0xffffffffu, is_out) & ri.run_mask;
+  const u32 fus = __ballot_sync(0xffffffffu, is_fused) & ri.run_mask;
+  const i64 sh = run_sum(fh, lane, ri.run_mask), sv = run_sum(fv, lane, ri.run_mask);
+  const u64 top_key = __shfl_sync(0xffffffffu, key, fus ? 31 - __clz(fus) : lane);   // highest fused lane = latest point
+  if (ri.tail && idx >= 0) {
+    if (outs) red_add(s.n_out + idx, (u32)__popc(outs), s.mc_off);
+    if (fus) {
+      red_add((u64*)(s.SH + idx), (u64)sh, s.mc_off);
+      red_add((u64*)(s.SV + idx), (u64)sv, s.mc_off);
+      red_add(s.cnt_fused + idx, (u32)__popc(fus), s.mc_off);
+      red_max(s.last + idx, top_key, s.mc_off);
+    }
   }
 }
 
@@ -483,21 +553,55 @@ k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const F
 template <int KT>
 __global__ void __launch_bounds__(256)
 k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, float* __restrict__ normal) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int W = c.W, C = c.C;
   const int K = KT ? KT : c.dilation;
-  const int HL = K + 3;                          // halo of the staged inputs
-  const int A = PT_Y + 2 * HL, B = PT_X + 2 * HL;
+  const int HL = K + 3;                          // row halo of the staged inputs
+  const int HLX = (HL + 3) & ~3;                 // column halo rounded up to 16 bytes: every staged row segment
+                                                 // starts on a 16-byte boundary, as the TMA bulk copy needs
+  const int A = PT_Y + 2 * HL, B = PT_X + 2 * HLX;
   constexpr int DA = PT_Y + 6, DB = PT_X + 6;
   float* s_up = smem;                            // A*B   upper_bound
-  float* s_mask = s_up + A * B;                  // A*B   raw mask = is_valid + is_upper_bound (CK.py:424)
-  float* s_dil = s_mask + A * B;                 // DA*DB dilated tile (+3 halo)
+  float* s_mask = s_up + A * B;                  // A*B   is_valid, then the raw mask = is_valid + is_upper_bound (CK.py:424)
+  float* s_iu = s_mask + A * B;                  // A*B   is_upper_bound (bulk path only)
+  float* s_dil = s_iu + A * B;                   // DA*DB dilated tile (+3 halo)
   unsigned long long* s_rowsel = reinterpret_cast<unsigned long long*>(s_dil + DA * DB + ((DA * DB) & 1));   // A words
+  unsigned long long* s_bar = s_rowsel + A;      // mbarrier of the bulk copies
   const float* up = map + 5 * C; const float* valid = map + 2 * C; const float* isup = map + 6 * C;
   const int r0 = blockIdx.y * PT_Y, c0 = blockIdx.x * PT_X;
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  // stage the two planes; per staged row also one 64-bit word whose bit b says "cell (a,b) may be
-  // SELECTED as a neighbour" (CK.py:432-434: is_inside && mask > 0.5), built with warp ballots (B <= 64)
+  // Stage upper_bound / is_valid / is_upper_bound for the tile + halo.  Interior tiles: one TMA bulk copy
+  // (cp.async.bulk, 16-byte aligned row segments of B floats) per plane and row, all completing on one mbarrier;
+  // tiles touching the left / right map edge, or maps whose row pitch is not a multiple of 16 bytes: plain loads.
+  const bool bulk = (W % 4 == 0) && c0 >= HLX && c0 + PT_X + HLX <= W;
+  if (bulk) {
+    const u32 sbar = (u32)__cvta_generic_to_shared(s_bar);
+    const int ra = max(0, HL - r0), rb = min(A, W - r0 + HL);          // staged rows that exist in the map: [ra, rb)
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbar), "r"((rb - ra) * 3 * B * 4) : "memory");
+    }
+    __syncthreads();
+    for (int e = tid; e < 3 * A; e += 256) {
+      const int pl = e / A, a = e - pl * A;
+      float* dstp = (pl == 0 ? s_up : pl == 1 ? s_mask : s_iu) + a * B;
+      if (a >= ra && a < rb) {
+        const float* src = (pl == 0 ? up : pl == 1 ? valid : isup) + (size_t)(r0 - HL + a) * W + (c0 - HLX);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((u32)__cvta_generic_to_shared(dstp)), "l"(src), "r"(B * 4), "r"(sbar) : "memory");
+      } else {
+        for (int b = 0; b < B; b++) dstp[b] = 0.f;                       // row outside the map
+      }
+    }
+    u32 ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(sbar), "r"(0) : "memory");
+    __syncthreads();
+  }
+  // raw mask + per staged row one 64-bit word whose bit b says "cell (a,b) may be SELECTED as a neighbour"
+  // (CK.py:432-434: is_inside && mask > 0.5), built with warp ballots (B <= 64)
   int any_sel = 0;
   for (int a = ty; a < A; a += 8) {
     const int r = r0 - HL + a;
@@ -505,16 +609,21 @@ k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, 
 #pragma unroll
     for (int ch = 0; ch < 2; ch++) {
       const int b = tx + 32 * ch;
-      const int cc = c0 - HL + b;
-      float u = 0.f, m = 0.f;
+      const int cc = c0 - HLX + b;
+      float m = 0.f;
       const bool in_stage = b < B;
-      if (in_stage && r >= 0 && r < W && cc >= 0 && cc < W) {
-        const int gi = r * W + cc;
-        u = __ldg(up + gi);
-        m = __fadd_rn(__ldg(valid + gi), __ldg(isup + gi));
+      if (bulk) {
+        if (in_stage) { m = __fadd_rn(s_mask[a * B + b], s_iu[a * B + b]); s_mask[a * B + b] = m; }
+      } else {
+        float u = 0.f;
+        if (in_stage && r >= 0 && r < W && cc >= 0 && cc < W) {
+          const int gi = r * W + cc;
+          u = __ldg(up + gi);
+          m = __fadd_rn(__ldg(valid + gi), __ldg(isup + gi));
+        }
+        if (in_stage) { s_up[a * B + b] = u; s_mask[a * B + b] = m; }
       }
       const bool sel = in_stage && r > 0 && r < W - 1 && cc > 0 && cc < W - 1 && m > 0.5f;
-      if (in_stage) { s_up[a * B + b] = u; s_mask[a * B + b] = m; }
       bits[ch] = __ballot_sync(0xffffffffu, sel);
     }
     if (tx == 0) s_rowsel[a] = ((unsigned long long)bits[1] << 32) | bits[0];
@@ -527,7 +636,7 @@ k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, 
     float out = 0.f;
     if (r >= 0 && r < W && cc >= 0 && cc < W) {
       if (cc >= K - 1 && cc <= W - K) {          // no wrapped neighbour can be selected: shared-memory path
-        const int sa = a + K, sb = b + K;        // position in the staged planes (HL - 3 == K)
+        const int sa = a + K, sb = b + HLX - 3;  // position in the staged planes (HL - 3 == K rows, HLX - 3 columns)
         out = s_up[sa * B + sb];
         if (any_sel && s_mask[sa * B + sb] < 0.5f) {
           // windows of selectable neighbours, one (2K+1)-bit word per row; first hit in
