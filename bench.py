@@ -60,7 +60,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except Exception:
@@ -144,7 +144,7 @@ def run_reference_arm(args):
     ms = 1e3 * sum(times) / len(times)
     val = n_sensors * PTS_PER_SENSOR / (ms * 1e-3) / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpoints/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "timed_steps": n_steps, "timed_warmup": n_warm, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "1024x1024 grid, 0.04 m, %d x 200k-pt LiDAR frame(s), raycast+overlap-clear on" % n_sensors,
                        "frames_per_s": 1e3 / ms},
@@ -336,14 +336,23 @@ def _main():
     dom = int(np.argmax(stage[:7]))
     # algorithmic bytes per launch of each stage (DESIGN.md "bytes per unit")
     N = PTS_PER_SENSOR
-    alg = {"index+error": 12 * N + 20 * N + 16 * N, "drift": 64, "fusion": 20 * N + 12 * N + 28 * N,
-           "record": 36 * C + 16 * C, "raycast": 20 * N + 16 * C, "finalize": 24 * C + 28 * C + 24 * C,
+    NV = int(st.n_valid_points)
+    # compulsory bytes per launch with the layout of DESIGN.md section 3 (each input once, each output once)
+    alg = {"index+error": 12 * N + 20 * N + 32 * NV + 16 * NV, "drift": 64, "fusion": 20 * N + 12 * NV + 28 * NV,
+           "record": 28 * C + 8 * C, "raycast": 32 * NV + 8 * C, "finalize": 24 * C + 24 * C + 12 * C,
            "post(dilate+cnn+normal)": 12 * C + 20 * C}
     dom_name = names[dom]
     ach = alg[dom_name] / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
     frame_bytes = 24 * N * world + 80 * C
+    traffic = None          # dram__bytes_read+write of the dominant kernel per launch, from the committed ncu capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+        if tr.get("kernel") == dom_name:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": hbm, "unit": "GB/s",
-                "frac": ach / hbm, "traffic": None, "peak_source": peak_src,
+                "frac": ach / hbm, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": float(stage[dom]), "kernel_share_of_frame": float(stage[dom] / max(stage[7], 1e-9)),
                 "frame_algorithmic_bytes": frame_bytes,
                 "frame_achieved_gbs": frame_bytes / (ms * 1e-3) / 1e9, "frame_frac": frame_bytes / (ms * 1e-3) / 1e9 / hbm,
