@@ -243,3 +243,59 @@ def test_config_e_independent_replicas(oracle_mod):
             om.move_to(t, R); om.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02); om.update_time()
         state, normal = ems[m].get_state()
         compare_state(state, normal, om, label=f"replica {m}")
+
+
+def test_edge_case_clouds(oracle_mod):
+    """empty / all-NaN / single-point / far-outside / non-finite clouds, and frames without time ticks"""
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = core_parameter(130)
+    em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+    R = np.eye(3, dtype=np.float32); t = np.array([0.1, -0.2, 1.0], np.float32)
+    base, _, _ = wl.lidar_cloud(0, 1, n_rings=24, n_az=500, max_range=4.0)
+    far = (np.random.default_rng(0).uniform(-400, 400, (3000, 3))).astype(np.float32)           # clamps to the border ring
+    weird = base[:2000].copy()
+    weird[::5, 0] = np.inf; weird[1::5, 1] = -np.inf; weird[2::5, 2] = 65520.0                   # beyond fp16 range
+    cases = [np.zeros((0, 3), np.float32), np.full((100, 3), np.nan, np.float32), base[:1].copy(), base, far, weird,
+             base[::3].copy(), base[::3].copy()]                                                  # the last two: no tick in between
+    for k, pts in enumerate(cases):
+        for m in (em, om):
+            m.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+        state, normal = em.get_state()
+        compare_state(state, normal, om, label=f"edge case {k}")
+        if len(pts):
+            idx, valid, inside = em.get_point_record(len(pts))
+            oi, ov, oin = om.last_point_record
+            ok = ~np.isnan(pts).any(1)
+            assert np.array_equal(idx[ok], oi[ok]) and np.array_equal(valid, ov) and np.array_equal(inside, oin), k
+        if k < 6:
+            for m in (em, om):
+                m.update_variance(); m.update_time()
+
+
+@pytest.mark.parametrize("dil", [0, 4])
+def test_unusual_dilation_sizes(oracle_mod, dil):
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = core_parameter(130, dilation_size=dil)
+    em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+    for f in range(2):
+        pts, R, t = wl.lidar_cloud(0, f, n_rings=24, n_az=500, max_range=4.0)
+        for m in (em, om):
+            m.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02); m.update_time()
+    state, normal = em.get_state()
+    compare_state(state, normal, om, label=f"dilation {dil}")
+
+
+def test_device_f64_rows_and_torch_input(oracle_mod):
+    import torch
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = core_parameter(130)
+    em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+    pts, R, t = wl.lidar_cloud(0, 2, n_rings=24, n_az=500, max_range=4.0)
+    wide = np.concatenate([pts.astype(np.float64), np.ones((len(pts), 4))], 1)
+    em.input_pointcloud(torch.from_numpy(wide).cuda(), ["x", "y", "z", "r", "g", "b", "a"], torch.from_numpy(R), t, 0.02, 0.02)
+    om.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+    state, normal = em.get_state()
+    compare_state(state, normal, om, label="device f64 rows")
