@@ -71,6 +71,7 @@ struct emap_handle {
   std::vector<int64_t> pend_n;
   int64_t pend_stride = 0;
   int pend_dtype = 0, pend_host = 0;
+  bool zero_copy_pending = false;      // the index pass reads the caller's pinned host buffer: sync before returning
   // export staging
   float* d_export = nullptr;
   // plugin scratch
@@ -241,8 +242,24 @@ int frame_begin(emap_handle* h, int32_t n_sensors, const void* const* points, co
   std::vector<const void*> dev_vec;
   const void** dp = dev_pts;
   if (n_sensors > 64) { dev_vec.resize(n_sensors); dp = dev_vec.data(); }
+  // Host clouds in page-locked memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) are read by the index
+  // kernel directly over PCIe (zero-copy): no staging copy, no copy-engine round trip.  Pageable memory is staged.
+  bool zero_copy = false;
+  if (!is_device_ptr) {
+    zero_copy = true;
+    for (int s = 0; s < n_sensors && zero_copy; s++) {
+      if (n[s] == 0) { dp[s] = points[s]; continue; }
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, points[s]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+        cudaGetLastError(); zero_copy = false;
+      } else dp[s] = at.devicePointer;
+    }
+  }
   if (is_device_ptr) {
     for (int s = 0; s < n_sensors; s++) dp[s] = points[s];
+  } else if (zero_copy) {
+    is_device_ptr = 1;                       // nothing to stage; the caller's buffer is read until the index pass ends
+    h->zero_copy_pending = true;
   } else {
     const int b = h->in_sel; h->in_sel ^= 1;
     size_t total = 0;
@@ -277,6 +294,7 @@ int frame_index(emap_handle* h) {
     if (rc) return rc;
   }
   if (h->pend_host) CK(cudaEventRecord(h->in_free[h->in_sel ^ 1], h->stream));
+  if (h->zero_copy_pending) CK(cudaEventRecord(h->copy_done, h->stream));      // caller's buffer is free after this point
   if (stage_mark(h, 1)) return EMAP_ERR_CUDA;
   h->phase = 1;
   return 0;
@@ -523,7 +541,8 @@ int emap_input_sensors(emap_handle* h, int32_t n_sensors, const void* const* poi
   if ((rc = frame_fuse(h))) return rc;
   if ((rc = frame_rays(h))) return rc;
   if ((rc = frame_finish(h))) return rc;
-  if (!is_device_ptr) CK(cudaEventSynchronize(h->copy_done));      // caller may reuse its host buffers on return
+  if (!is_device_ptr || h->zero_copy_pending) CK(cudaEventSynchronize(h->copy_done));   // caller may reuse its host buffers on return
+  h->zero_copy_pending = false;
   return EMAP_OK;
 }
 
@@ -543,10 +562,13 @@ int emap_shard_begin(emap_handle* h, int32_t n_sensors, const void* const* point
   if (!points || !n || !R || !t) return fail(h, EMAP_ERR_INVALID, "emap_shard_begin: null argument");
   int rc = frame_begin(h, n_sensors, points, n, row_stride, dtype, is_device_ptr, R, t, global_point_offset, pn, on);
   if (rc) return rc;
-  if (!is_device_ptr) CK(cudaEventSynchronize(h->copy_done));      // caller may reuse its host buffers on return
+  if (!is_device_ptr && !h->zero_copy_pending) CK(cudaEventSynchronize(h->copy_done));   // staged copy done: host buffers reusable
   // multicast mode: every rank must have reset its frame scalars before anyone pushes -> the caller runs a
   // cross-rank barrier and then emap_shard_phase(h, 0); NCCL mode: index right away
-  return h->attached ? 0 : frame_index(h);
+  if (h->attached) return 0;
+  rc = frame_index(h);
+  if (!rc && h->zero_copy_pending) { CK(cudaEventSynchronize(h->copy_done)); h->zero_copy_pending = false; }
+  return rc;
 }
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -628,7 +650,9 @@ int emap_shard_phase(emap_handle* h, int32_t phase) {
   ENTER(h);
   if (phase == 0) {
     if (h->phase != -1) return fail(h, EMAP_ERR_STATE, "phase 0 must follow emap_shard_begin on an attached handle");
-    return frame_index(h);
+    int rc0 = frame_index(h);
+    if (!rc0 && h->zero_copy_pending) { CK(cudaEventSynchronize(h->copy_done)); h->zero_copy_pending = false; }
+    return rc0;
   }
   if (phase == 1) {
     if (h->phase != 1) return fail(h, EMAP_ERR_STATE, "phase 1 must follow emap_shard_begin");
