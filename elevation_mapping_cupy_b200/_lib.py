@@ -71,6 +71,11 @@ SIGNATURES = {
     "emap_min_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                   C.POINTER(C.c_int32)]),
     "emap_smooth_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "emap_max_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                  C.POINTER(C.c_int32)]),
+    "emap_erode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "emap_robot_centric_elevation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_double, C.c_double, C.c_int32]),
     "emap_inpaint": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "emap_sync": (C.c_int, [C.c_void_p]),
     "emap_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

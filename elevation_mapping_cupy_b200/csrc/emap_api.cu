@@ -847,9 +847,61 @@ int emap_set_state(emap_handle* h, const float* map_host, const float* normal_ho
 }
 
 // ---- plugins ---------------------------------------------------------------------------------
+static int minmax_filter(emap_handle* h, const float* elevation, const float* is_valid, float* out, int32_t k,
+                         int32_t iteration_n, int32_t* iterations_run, int is_max);
+
 int emap_min_filter(emap_handle* h, const float* elevation, const float* is_valid, float* out, int32_t k, int32_t iteration_n,
                     int32_t* iterations_run) {
   ENTER(h);
+  return minmax_filter(h, elevation, is_valid, out, k, iteration_n, iterations_run, 0);
+}
+
+int emap_max_filter(emap_handle* h, const float* elevation, const float* is_valid, float* out, int32_t k, int32_t iteration_n,
+                    int32_t* iterations_run) {
+  ENTER(h);
+  return minmax_filter(h, elevation, is_valid, out, k, iteration_n, iterations_run, 1);
+}
+
+int emap_erode(emap_handle* h, const float* layer, float* out, int32_t kernel_size, int32_t iterations, int32_t reverse) {
+  ENTER(h);
+  if (!layer || !out || kernel_size < 1 || kernel_size > 31 || iterations < 1 || iterations > 64)
+    return fail(h, EMAP_ERR_INVALID, "emap_erode: bad argument");
+  int rc = alloc_plugin_scratch(h);
+  if (rc) return rc;
+  if (h->pl_cnt_cap < 2) {
+    if (h->pl_cnt) cudaFree(h->pl_cnt);
+    h->pl_cnt = nullptr; h->pl_cnt_cap = 0;
+    CK(cudaMalloc(&h->pl_cnt, sizeof(int) * 32));
+    h->pl_cnt_cap = 32;
+  }
+  const u32 init[2] = {0xffffffffu, 0u};
+  CK(cudaMemcpyAsync(h->pl_cnt, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  const int nb = cdiv(h->dc.C, 256);
+  k_layer_minmax<<<nb, 256, 0, h->stream>>>(h->dc, layer, reverse, (u32*)h->pl_cnt);
+  LAUNCH_CHECK();
+  const int ks = kernel_size + (iterations - 1) * (kernel_size - 1), anchor = (kernel_size / 2) * iterations;
+  const float* src = layer;
+  if (layer == out) {        // in-place call: erode from a copy
+    CK(cudaMemcpyAsync(h->pl[0], layer, sizeof(float) * (size_t)h->dc.C, cudaMemcpyDeviceToDevice, h->stream));
+    src = h->pl[0];
+  }
+  k_erode<<<nb, 256, 0, h->stream>>>(h->dc, src, out, ks, anchor, reverse, (const u32*)h->pl_cnt);
+  LAUNCH_CHECK();
+  return EMAP_OK;
+}
+
+int emap_robot_centric_elevation(emap_handle* h, const float* elevation, const float* is_valid, const float R[9], float* out,
+                                 double resolution, double threshold, int32_t use_threshold) {
+  ENTER(h);
+  if (!elevation || !is_valid || !R || !out) return fail(h, EMAP_ERR_INVALID, "null argument");
+  k_robot_centric<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, elevation, is_valid, out, R[6], R[7], R[8], resolution,
+                                                              threshold, use_threshold);
+  LAUNCH_CHECK();
+  return EMAP_OK;
+}
+
+static int minmax_filter(emap_handle* h, const float* elevation, const float* is_valid, float* out, int32_t k,
+                         int32_t iteration_n, int32_t* iterations_run, int is_max) {
   if (!elevation || !is_valid || !out || k < 0 || k > 16 || iteration_n < 1)
     return fail(h, EMAP_ERR_INVALID, "emap_min_filter: bad argument");
   int rc = alloc_plugin_scratch(h);
@@ -869,7 +921,7 @@ int emap_min_filter(emap_handle* h, const float* elevation, const float* is_vali
   for (int it = 0; it < iteration_n; it++) {
     const bool even = (it & 1) == 0;
     k_min_filter_iter<<<nb, 256, 0, h->stream>>>(h->dc, k, is_valid, even ? hA : hB, even ? mA : mB, even ? hB : hA,
-                                                  even ? mB : mA, h->pl_cnt, it);
+                                                  even ? mB : mA, h->pl_cnt, it, is_max);
     LAUNCH_CHECK();
   }
   k_min_filter_final<<<nb, 256, 0, h->stream>>>(h->dc, hA, mA, hB, mB, h->pl_cnt, iteration_n, out, h->pl_cnt + iteration_n);

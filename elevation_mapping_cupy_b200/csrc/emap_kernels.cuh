@@ -848,17 +848,33 @@ k_export(const DevCfg c, const float* __restrict__ map, const float* __restrict_
 // plugins/min_filter.py:57-82 with Jacobi order (reads iteration k-1, writes iteration k).
 // `unfilled[it]` counts cells whose mask is still <= 0.5 after iteration it; an iteration whose
 // predecessor left none is skipped on the device (min_filter.py:115 breaks on the host instead).
+// is_max = 1: plugins/max_filter.py:68-88 -- same stencil with max, and the fill test looks at the CURRENT mask
+// (max_filter.py:102-108 passes copies of the running arrays), where min_filter keeps testing the ORIGINAL one.
 __global__ void __launch_bounds__(256)
 k_min_filter_iter(const DevCfg c, int k, const float* __restrict__ mask0, const float* __restrict__ in_h,
                   const float* __restrict__ in_m, float* __restrict__ out_h, float* __restrict__ out_m,
-                  int* __restrict__ unfilled, int it) {
+                  int* __restrict__ unfilled, int it, int is_max) {
   if (it > 0 && unfilled[it - 1] == 0) { if (blockIdx.x == 0 && threadIdx.x == 0) unfilled[it] = 0; return; }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int miss = 0;
   if (i < c.C) {
     const int W = c.W;
     float h = in_h[i], m = in_m[i];
-    if (mask0[i] < 0.5f) {
+    if (is_max) {
+      if (m < 0.5f) {
+        float mv = -1000000.0f;
+        for (int dy = -k; dy <= k; dy++)
+          for (int dx = -k; dx <= k; dx++) {
+            const int idx = i + W * dy + dx;
+            if (idx < 0 || idx >= c.C) continue;
+            const int ix = idx / W, iy = idx - ix * W;
+            if (ix <= 0 || ix >= W - 1 || iy <= 0 || iy >= W - 1) continue;
+            const float val = in_h[idx];
+            if (in_m[idx] > 0.5f && val > mv) mv = val;
+          }
+        if (mv > -1000000.f + 1.f) { h = mv; m = 0.6f; }
+      }
+    } else if (mask0[i] < 0.5f) {
       float mv = 1000000.0f;
       for (int dy = -k; dy <= k; dy++)
         for (int dx = -k; dx <= k; dx++) {
@@ -905,4 +921,64 @@ k_box3(const DevCfg c, const float* __restrict__ in, float* __restrict__ out, in
   else { ia = r * W + (cc == 0 ? 0 : cc - 1); ib = r * W + (cc == W - 1 ? W - 1 : cc + 1); }
   const double sacc = __dadd_rn(__dadd_rn(__dmul_rn((double)in[ia], w), __dmul_rn((double)in[i], w)), __dmul_rn((double)in[ib], w));
   out[i] = (float)sacc;
+}
+
+// ------------------------------------------------------------------------------------------
+// plugins/erosion.py:96-113: min / max of the (optionally reversed) layer, 8-bit normalisation, cv.erode with a
+// ones(k,k) kernel (OpenCV folds `iterations` of a full rectangle into ONE erosion with a rectangle of side
+// k + (iterations-1)(k-1) anchored at (k/2)*iterations; pixels outside the image do not constrain the minimum),
+// de-normalisation.  mm = {min, max} as order-preserving keys.
+__global__ void __launch_bounds__(256)
+k_layer_minmax(const DevCfg c, const float* __restrict__ in, int reverse, u32* __restrict__ mm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 lo = 0xffffffffu, hi = 0u;
+  if (i < c.C) {
+    float x = in[i];
+    if (reverse) x = __fsub_rn(1.0f, x);
+    lo = hi = fkey(x);
+  }
+  lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+  if ((threadIdx.x & 31) == 0) { atomicMin(mm, lo); atomicMax(mm + 1, hi); }
+}
+__global__ void __launch_bounds__(256)
+k_erode(const DevCfg c, const float* __restrict__ in, float* __restrict__ out, int ks, int anchor, int reverse,
+        const u32* __restrict__ mm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.C) return;
+  const int W = c.W, r = i / W, cc = i - r * W;
+  const float mn = funkey(mm[0]), mx = funkey(mm[1]);
+  const float span = (float)((double)mx - (double)mn);            // python float difference, used as float32
+  int best = 255;
+  for (int dy = -anchor; dy < ks - anchor; dy++) {
+    const int rr = r + dy;
+    if (rr < 0 || rr >= W) continue;
+    for (int dx = -anchor; dx < ks - anchor; dx++) {
+      const int c2 = cc + dx;
+      if (c2 < 0 || c2 >= W) continue;
+      float x = in[rr * W + c2];
+      if (reverse) x = __fsub_rn(1.0f, x);
+      const int q = (int)(unsigned char)__float2int_rz(__fdiv_rn(__fmul_rn(__fsub_rn(x, mn), 255.0f), span));
+      best = min(best, q);
+    }
+  }
+  float y = __fadd_rn(__fdiv_rn(__fmul_rn((float)best, span), 255.0f), mn);
+  if (reverse) y = __fsub_rn(1.0f, y);
+  out[i] = y;
+}
+
+// plugins/robot_centric_elevation.py:66-83: z of the cell in the base frame, optionally thresholded.
+__global__ void __launch_bounds__(256)
+k_robot_centric(const DevCfg c, const float* __restrict__ elev, const float* __restrict__ valid, float* __restrict__ out,
+                float r6, float r7, float r8, double resolution, double threshold, int use_threshold) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.C) return;
+  const float rz = elev[i];
+  float o = rz;                                                   // self.min_filtered = elevation_map[0].copy()
+  if (valid[i] > 0.5f) {
+    const float rx = (float)((double)(i / c.W) * resolution), ry = (float)((double)(i % c.W) * resolution);
+    const float zb = __fmaf_rn(r8, rz, __fmaf_rn(r6, rx, __fmul_rn(r7, ry)));   // r0*x + r1*y + r2*z, nvcc contraction
+    if (use_threshold) o = ((double)zb >= threshold) ? 1.0f : 0.0f;
+    else o = zb;
+  }
+  out[i] = o;
 }

@@ -183,6 +183,14 @@ int emap_set_state(emap_handle* h, const float* map_host, const float* normal_ho
 int emap_min_filter(emap_handle* h, const float* elevation, const float* is_valid, float* out, int32_t dilation_size,
                     int32_t iteration_n, int32_t* iterations_run);
 int emap_smooth_filter(emap_handle* h, const float* in, float* out);
+/* plugins/max_filter.py:36-113 (Jacobi max-fill), plugins/erosion.py:96-113 (8-bit normalise, cv.erode with a
+ * ones(kernel_size) kernel `iterations` times, de-normalise; optional 1-x reversal), and
+ * plugins/robot_centric_elevation.py:66-121 (cell height in the base frame, R row-major 3x3). */
+int emap_max_filter(emap_handle* h, const float* elevation, const float* is_valid, float* out, int32_t dilation_size,
+                    int32_t iteration_n, int32_t* iterations_run);
+int emap_erode(emap_handle* h, const float* layer, float* out, int32_t kernel_size, int32_t iterations, int32_t reverse);
+int emap_robot_centric_elevation(emap_handle* h, const float* elevation, const float* is_valid, const float R[9], float* out,
+                                 double resolution, double threshold, int32_t use_threshold);
 int emap_inpaint(emap_handle* h, const float* elevation, const float* is_valid, float* out, int32_t method);
 
 /* ---- plumbing ---- */

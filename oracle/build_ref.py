@@ -88,6 +88,31 @@ def _min_filter_rec(cell_n, dilation_size):
     return obj.min_filter_kernel
 
 
+def _plugin_rec(fname, cls, attr, **ctor):
+    """Kernel built inside a plugin class constructor (the module imports .plugin_manager, which needs ruamel)."""
+    src = open(os.path.join(REF_ROOT, "plugins", fname)).read()
+    for imp in ("from .plugin_manager import PluginBase", "from elevation_mapping_cupy.plugins.plugin_manager import PluginBase"):
+        src = src.replace(imp, "class PluginBase:\n    def __init__(self, *a, **k):\n        pass\n")
+    stub = types.ModuleType("cupy")
+    stub.ElementwiseKernel = lambda in_params, out_params, operation, name="k", preamble="", **kw: _Rec(
+        in_params, out_params, operation, name, preamble)
+    stub.ndarray = object
+    stub.float32 = "float32"
+    stub.zeros = lambda *a, **k: None
+    saved = sys.modules.get("cupy")
+    sys.modules["cupy"] = stub
+    try:
+        ns = {}
+        exec(compile(src, fname, "exec"), ns)
+        obj = ns[cls](**ctor)
+    finally:
+        if saved is None:
+            sys.modules.pop("cupy", None)
+        else:
+            sys.modules["cupy"] = saved
+    return getattr(obj, attr)
+
+
 def _params(rec):
     """'raw U a, raw T b' -> [('U','a'), ...] for in and out."""
     def parse(s):
@@ -152,6 +177,14 @@ def generate(P, gpu):
         "dilation_filter": ck.dilation_filter_kernel(W, W, P["dilation_size"]),
         "normal_filter": ck.normal_filter_kernel(W, W, P["resolution"]),
         "min_filter": _min_filter_rec(W, P.get("min_filter_dilation_size", 1)),
+        "max_filter": _plugin_rec("max_filter.py", "MaxFilter", "max_filter_kernel", cell_n=W,
+                                  dilation_size=P.get("min_filter_dilation_size", 1), iteration_n=1),
+        "base_elevation_thr": _plugin_rec("robot_centric_elevation.py", "RobotCentricElevation", "base_elevation_kernel",
+                                          cell_n=W, resolution=P["resolution"], threshold=P.get("rce_threshold", 1.1),
+                                          use_threshold=True),
+        "base_elevation_raw": _plugin_rec("robot_centric_elevation.py", "RobotCentricElevation", "base_elevation_kernel",
+                                          cell_n=W, resolution=P["resolution"], threshold=P.get("rce_threshold", 1.1),
+                                          use_threshold=False),
     }
     src = '#include "ref_shim.h"\n'
     for fn, rec in recs.items():

@@ -15,6 +15,7 @@ def ref_dict(param: Parameter, min_filter_dilation_size=1):
             "traversability_inlier", "max_variance", "initial_variance", "dilation_size"]
     d = {k: getattr(param, k) for k in keys}
     d["min_filter_dilation_size"] = min_filter_dilation_size
+    d["rce_threshold"] = 1.1          # tests/plugin_config.yaml of the reference
     return d
 
 

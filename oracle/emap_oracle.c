@@ -307,6 +307,54 @@ int oracle_min_filter(int W, int k, int iteration_n, const float* map, const flo
     return it;
 }
 
+/* plugins/max_filter.py:68-113: Jacobi (the reference copies both arrays before every launch), fill test on
+ * the CURRENT mask. */
+int oracle_max_filter(int W, int k, int iteration_n, const float* map, const float* mask, float* out) {
+    int C = W * W;
+    float* a = (float*)malloc(sizeof(float) * C), *am = (float*)malloc(sizeof(float) * C);
+    float* b = (float*)malloc(sizeof(float) * C), *bm = (float*)malloc(sizeof(float) * C);
+    memcpy(a, map, sizeof(float) * C); memcpy(am, mask, sizeof(float) * C);
+    int it = 0;
+    for (; it < iteration_n; it++) {
+        memcpy(b, a, sizeof(float) * C); memcpy(bm, am, sizeof(float) * C);
+        for (int i = 0; i < C; i++) {
+            if (am[i] < 0.5f) {
+                float mv = -1000000.0f;
+                for (int dy = -k; dy <= k; dy++)
+                    for (int dx = -k; dx <= k; dx++) {
+                        int idx = i + W * dy + dx;
+                        if (!is_inside_rel(W, idx)) continue;
+                        if (am[idx] > 0.5f && a[idx] > mv) mv = a[idx];
+                    }
+                if (mv > -1000000.f + 1.f) { b[i] = mv; bm[i] = 0.6f; }
+            }
+        }
+        float* t = a; a = b; b = t; t = am; am = bm; bm = t;
+        int all = 1;
+        for (int i = 0; i < C; i++) if (!(am[i] > 0.5f)) { all = 0; break; }
+        if (all) { it++; break; }
+    }
+    for (int i = 0; i < C; i++) out[i] = am[i] > 0.5f ? a[i] : NAN;
+    free(a); free(am); free(b); free(bm);
+    return it;
+}
+
+/* plugins/robot_centric_elevation.py:54-83 */
+void oracle_robot_centric(int W, double resolution, double threshold, int use_threshold, const float* elev,
+                          const float* valid, const float* R, float* out) {
+    for (int i = 0; i < W * W; i++) {
+        float rz = elev[i];
+        out[i] = rz;
+        if (valid[i] > 0.5f) {
+            float rx = (float)((double)(i / W) * resolution), ry = (float)((double)(i % W) * resolution);
+            /* FMAD: r0*x + r1*y + r2*z -> fma(r2,z, fma(r0,x, r1*y)) */
+            float zb = fmaf(R[8], rz, fmaf(R[6], rx, R[7] * ry));
+            if (use_threshold) out[i] = ((double)zb >= threshold) ? 1.0f : 0.0f;
+            else out[i] = zb;
+        }
+    }
+}
+
 /* plugins/smooth_filter.py:57-58: two passes of a 3x3 uniform filter with
  * scipy.ndimage 'reflect' boundary (d c b a | a b c d | d c b a), separable,
  * axis 0 then axis 1; each 1-D pass accumulates in double and stores fp32. */

@@ -371,6 +371,38 @@ def min_filter(W, k, iteration_n, h, mask):
     return out, it
 
 
+def max_filter(W, k, iteration_n, h, mask):
+    out = np.zeros((W, W), np.float32)
+    lib().oracle_max_filter.restype = C.c_int
+    it = lib().oracle_max_filter(C.c_int(W), C.c_int(k), C.c_int(iteration_n), _p(np.ascontiguousarray(h, np.float32)),
+                                 _p(np.ascontiguousarray(mask, np.float32)), _p(out))
+    return out, it
+
+
+def robot_centric(W, resolution, threshold, use_threshold, elev, valid, R):
+    out = np.zeros((W, W), np.float32)
+    lib().oracle_robot_centric(C.c_int(W), C.c_double(resolution), C.c_double(threshold), C.c_int(int(use_threshold)),
+                               _p(np.ascontiguousarray(elev, np.float32)), _p(np.ascontiguousarray(valid, np.float32)),
+                               _p(np.ascontiguousarray(R, np.float32).reshape(9)), _p(out))
+    return out
+
+
+def erosion_cv2(layer, kernel_size=3, iterations=1, reverse=False):
+    """plugins/erosion.py:96-113 verbatim (OpenCV on the host)."""
+    import cv2 as cv
+    layer_np = np.asarray(layer, np.float32)
+    kernel = np.ones((kernel_size, kernel_size), np.uint8)
+    if reverse:
+        layer_np = 1 - layer_np
+    layer_min = float(layer_np.min()); layer_max = float(layer_np.max())
+    norm = ((layer_np - layer_min) * 255 / (layer_max - layer_min)).astype("uint8")
+    er = cv.erode(norm, kernel, iterations=iterations)
+    er = er.astype(np.float32) * (layer_max - layer_min) / 255 + layer_min
+    if reverse:
+        er = 1 - er
+    return er
+
+
 def smooth(W, h):
     out = np.zeros((W, W), np.float32)
     lib().oracle_smooth(C.c_int(W), _p(np.ascontiguousarray(h, np.float32)), _p(out))

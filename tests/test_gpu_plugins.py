@@ -102,3 +102,60 @@ def test_move_and_shift_match_oracle(oracle_mod):
     em.clear(); om.clear()
     state, _ = em.get_state()
     assert np.array_equal(state, om.elevation_map)
+
+
+def test_star_plugins_match_oracle(oracle_mod):
+    """max_filter, erosion (vs the reference's literal cv2 code), robot_centric_elevation, max_layer_filter"""
+    import torch
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200.plugins.max_filter import MaxFilter
+    from elevation_mapping_cupy_b200.plugins.erosion import Erosion
+    from elevation_mapping_cupy_b200.plugins.robot_centric_elevation import RobotCentricElevation
+    from elevation_mapping_cupy_b200.plugins.max_layer_filter import MaxLayerFilter
+    W = 202
+    p = core_parameter(W)
+    em = _mk(p)
+    st = _random_state(W, 21, 0.3)
+    rng = np.random.default_rng(2)
+    st[3] = rng.random((W, W)).astype(np.float32)
+    em.set_state(st)
+    names = em.layer_names
+    # max_filter
+    out = MaxFilter(cell_n=W, dilation_size=1, iteration_n=6, engine=em)(em.elevation_map, names, None, []).cpu().numpy()
+    ref, _ = oracle_mod.max_filter(W, 1, 6, st[0], st[2])
+    assert np.array_equal(np.isnan(out), np.isnan(ref)) and np.array_equal(np.nan_to_num(out), np.nan_to_num(ref))
+    # erosion: default YAML of the reference (kernel 3, 1 iteration, reverse) and a multi-iteration even kernel
+    for ks, it, rev in ((3, 1, True), (3, 3, False), (4, 2, False), (5, 1, True)):
+        out = Erosion(input_layer_name="traversability", kernel_size=ks, iterations=it, reverse=rev, engine=em)(
+            em.elevation_map, names, None, [], None, []).cpu().numpy()
+        ref = oracle_mod.erosion_cv2(st[3], ks, it, rev)
+        assert np.array_equal(out, ref.astype(np.float32)), (ks, it, rev, np.abs(out - ref).max())
+    # robot_centric_elevation
+    R = np.array([[0.9, 0.1, -0.2], [0.0, 1.0, 0.1], [0.15, -0.12, 0.97]], np.float32)
+    for thr in (True, False):
+        out = RobotCentricElevation(cell_n=W, resolution=0.04, threshold=1.1, use_threshold=thr, engine=em)(
+            em.elevation_map, names, None, [], None, [], R).cpu().numpy()
+        ref = oracle_mod.robot_centric(W, 0.04, 1.1, thr, st[0], st[2], R)
+        assert np.array_equal(out, ref), thr
+    # max_layer_filter (element-wise algebra)
+    plug = MaxLayerFilter(cell_n=W, layers=["traversability", "variance"], reverse=[True, False], min_or_max="max",
+                          thresholds=[False, 0.04], scales=[2.0, 1.0], default_value=0.5)
+    out = plug(em.elevation_map, names, None, [], None, []).cpu().numpy()
+    a = np.where(st[3] == 0.0, np.float32(0.5), st[3]); a = (np.float32(1.0) - a) * np.float32(2.0)
+    b = np.where(st[1] == 0.0, np.float32(0.5), st[1]); b = np.where(b > np.float32(0.04), np.float32(1), np.float32(0))
+    assert np.array_equal(out, np.maximum(a, b).astype(np.float32))
+
+
+def test_default_plugin_yaml_layers_export():
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = core_parameter(202)
+    em = _mk(p)
+    pts, R, t = wl.lidar_cloud(0, 0, n_rings=32, n_az=625, max_range=8.0)
+    em.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+    data = np.zeros((200, 200), np.float32)
+    for name in em.plugin_manager.layer_names:
+        assert em.exists_layer(name)
+        em.get_map_with_name_ref(name, data)
+        assert np.isfinite(data).any(), name
+    assert "erosion" in em.plugin_manager.layer_names

@@ -140,3 +140,38 @@ def test_dilation_and_normal_against_reference_source(oracle_mod):
     ref_mf = rm.min_filter(1)
     ours_mf, _ = oracle_mod.min_filter(W, 1, 1, h, m2)
     assert np.array_equal(np.nan_to_num(ours_mf), np.nan_to_num(ref_mf))
+
+
+def test_star_plugin_oracles_against_reference_source(oracle_mod):
+    """max_filter / robot_centric_elevation restatements vs the reference's kernels (host build of their source)."""
+    import ctypes as C
+    p = core_parameter(130)
+    try:
+        rm = oracle_mod.RefKernelMap(p, "core130")
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not prebuilt and /root/reference absent")
+    W = 130
+    rng = np.random.default_rng(8)
+    h = rng.standard_normal((W, W)).astype(np.float32)
+    m = (rng.random((W, W)) < 0.3).astype(np.float32)
+    _p = oracle_mod._p
+    # max_filter.py:100-113: every launch reads COPIES of the running arrays
+    cur_h, cur_m = h.copy(), m.copy()
+    for _ in range(4):
+        ih, im = cur_h.copy(), cur_m.copy()
+        rm.lib.ref_max_filter(C.c_longlong(W * W), _p(ih), _p(im), _p(cur_h), _p(cur_m), C.c_int(0))
+        if (cur_m > 0.5).all():
+            break
+    ref = np.where(cur_m > 0.5, cur_h, np.nan)
+    ours, _ = oracle_mod.max_filter(W, 1, 4, h, m)
+    assert np.array_equal(np.nan_to_num(ours, nan=-7), np.nan_to_num(ref, nan=-7))
+    # robot_centric_elevation.py:118-121
+    R = np.array([[0.9, 0.1, -0.2], [0.0, 1.0, 0.1], [0.15, -0.12, 0.97]], np.float32)
+    for thr, fn in ((True, rm.lib.ref_base_elevation_thr), (False, rm.lib.ref_base_elevation_raw)):
+        out = h.copy()
+        fn(C.c_longlong(W * W), _p(h), _p(m), _p(np.ascontiguousarray(R.reshape(9))), _p(out), C.c_int(0))
+        ours = oracle_mod.robot_centric(W, p.resolution, 1.1, thr, h, m, R)
+        if thr:
+            assert np.array_equal(ours, out)
+        else:       # host build has no FMA contraction: last-ulp differences
+            assert np.abs(ours - out).max() <= 5e-7 * max(1.0, np.abs(out).max())
