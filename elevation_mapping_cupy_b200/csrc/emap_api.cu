@@ -107,6 +107,23 @@ namespace {
     }                                                                                     \
   } while (0)
 
+// launch with programmatic stream serialisation (PDL), see pdl_trigger / pdl_wait in emap_kernels.cuh
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+#define PDL(kern, grid, block, smem, ...)                                                         \
+  do {                                                                                            \
+    cudaError_t le_ = launch_pdl(kern, dim3(grid), dim3(block), (size_t)(smem), h->stream, __VA_ARGS__); \
+    if (le_ != cudaSuccess) { h->err = std::string("kernel launch: ") + cudaGetErrorString(le_); return EMAP_ERR_CUDA; } \
+  } while (0)
+
 inline float h16_host(float x) { return __half2float(__float2half_rn(x)); }
 
 inline int cdiv(i64 a, int b) { return (int)((a + b - 1) / b); }
@@ -198,8 +215,8 @@ int stage_mark(emap_handle* h, int k) {
 template <typename T>
 int launch_index(emap_handle* h, const Pose& q, const T* pts, i64 n, i64 stride, i64 off, int sensor) {
   if (n <= 0) return 0;
-  k_index_error<T><<<cdiv(n, 256), 256, 0, h->stream>>>(h->dc, q, pts, n, stride, h->xyzv + off, h->pidx + off, h->map,
-                                                           h->sc, h->fs, h->rays + off, h->ray_ctl + 2 * (h->ray_sel * h->ray_ctl_cap + sensor));
+  PDL(k_index_error<T>, cdiv(n, 256), 256, 0, h->dc, q, pts, n, stride, h->xyzv + off, h->pidx + off, (const float*)h->map,
+      h->sc, h->fs, h->rays + off, h->ray_ctl + 2 * (h->ray_sel * h->ray_ctl_cap + sensor));
   LAUNCH_CHECK();
   return 0;
 }
@@ -301,14 +318,14 @@ int frame_index(emap_handle* h) {
 }
 
 int frame_fuse(emap_handle* h) {
-  k_drift<<<1, 32, 0, h->stream>>>(h->dc, h->fs, h->pos_noise, h->ori_noise,
-                                   h->overlap_override ? h->overlap_z_override : h->poses[0].t[2], 1,
-                                   h->ray_ctl + 2 * ((h->ray_sel ^ 1) * h->ray_ctl_cap), 2 * h->ray_ctl_cap);
+  PDL(k_drift, 1, 32, 0, h->dc, h->fs, h->pos_noise, h->ori_noise,
+      h->overlap_override ? h->overlap_z_override : h->poses[0].t[2], 1,
+      h->ray_ctl + 2 * ((h->ray_sel ^ 1) * h->ray_ctl_cap), 2 * h->ray_ctl_cap);
   LAUNCH_CHECK();
   if (stage_mark(h, 2)) return EMAP_ERR_CUDA;
   if (h->n_points > 0) {
-    k_fuse<<<cdiv(h->n_points, 256), 256, 0, h->stream>>>(h->dc, h->n_points, h->global_off, h->xyzv, h->pidx, h->map,
-                                                            h->sc, h->fs);
+    PDL(k_fuse, cdiv(h->n_points, 256), 256, 0, h->dc, h->n_points, h->global_off, (const float4*)h->xyzv,
+        (const int*)h->pidx, (const float*)h->map, h->sc, (const FrameScalars*)h->fs);
     LAUNCH_CHECK();
   }
   if (stage_mark(h, 3)) return EMAP_ERR_CUDA;
@@ -318,8 +335,8 @@ int frame_fuse(emap_handle* h) {
 
 int frame_rays(emap_handle* h) {
   if (h->dc.visibility) {
-    if (h->dc.C % 4 == 0) k_record<4><<<cdiv(h->dc.C / 4, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs);
-    else k_record<1><<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs);
+    if (h->dc.C % 4 == 0) PDL(k_record<4>, cdiv(h->dc.C / 4, 256), 256, 0, h->dc, (const float*)h->map, h->sc, (const FrameScalars*)h->fs);
+    else PDL(k_record<1>, cdiv(h->dc.C, 256), 256, 0, h->dc, (const float*)h->map, h->sc, (const FrameScalars*)h->fs);
     LAUNCH_CHECK();
     if (stage_mark(h, 4)) return EMAP_ERR_CUDA;
     const size_t sm = sizeof(float) * (size_t)((h->dc.n_steps + 31) & ~31);
@@ -329,11 +346,11 @@ int frame_rays(emap_handle* h) {
       // persistent grid: enough CTAs to fill every SM, never more than one warp per possible ray
       const int grid = (int)std::min<i64>((i64)h->n_sm * h->rc_blocks_per_sm, (n + 3) / 4);
       if (h->count_rays)
-        k_raycast<true><<<grid, RC_THREADS, sm, h->stream>>>(h->dc, h->poses[s], h->rays + h->offs[s], h->ray_ctl + 2 * (h->ray_sel * h->ray_ctl_cap + (int)s),
-                                                               h->map, h->normal, h->sc, h->steps, h->fs);
+        PDL(k_raycast<true>, grid, RC_THREADS, sm, h->dc, h->poses[s], (const Ray*)(h->rays + h->offs[s]), h->ray_ctl + 2 * (h->ray_sel * h->ray_ctl_cap + (int)s),
+            (const float*)h->map, (const float*)h->normal, h->sc, (const float*)h->steps, h->fs);
       else
-        k_raycast<false><<<grid, RC_THREADS, sm, h->stream>>>(h->dc, h->poses[s], h->rays + h->offs[s], h->ray_ctl + 2 * (h->ray_sel * h->ray_ctl_cap + (int)s),
-                                                                h->map, h->normal, h->sc, h->steps, h->fs);
+        PDL(k_raycast<false>, grid, RC_THREADS, sm, h->dc, h->poses[s], (const Ray*)(h->rays + h->offs[s]), h->ray_ctl + 2 * (h->ray_sel * h->ray_ctl_cap + (int)s),
+            (const float*)h->map, (const float*)h->normal, h->sc, (const float*)h->steps, h->fs);
       LAUNCH_CHECK();
     }
   } else if (stage_mark(h, 4)) return EMAP_ERR_CUDA;
@@ -352,10 +369,10 @@ int launch_post(emap_handle* h) {
   dim3 grid(cdiv(h->dc.W, PT_X), cdiv(h->dc.W, PT_Y));
   const size_t sm = post_smem(h->dc);
   switch (h->dc.dilation) {
-    case 1: k_post<1><<<grid, 256, sm, h->stream>>>(h->dc, h->map, h->trav_input, h->normal); break;
-    case 2: k_post<2><<<grid, 256, sm, h->stream>>>(h->dc, h->map, h->trav_input, h->normal); break;
-    case 3: k_post<3><<<grid, 256, sm, h->stream>>>(h->dc, h->map, h->trav_input, h->normal); break;
-    default: k_post<0><<<grid, 256, sm, h->stream>>>(h->dc, h->map, h->trav_input, h->normal); break;
+    case 1: PDL(k_post<1>, grid, 256, sm, h->dc, h->map, h->trav_input, h->normal); break;
+    case 2: PDL(k_post<2>, grid, 256, sm, h->dc, h->map, h->trav_input, h->normal); break;
+    case 3: PDL(k_post<3>, grid, 256, sm, h->dc, h->map, h->trav_input, h->normal); break;
+    default: PDL(k_post<0>, grid, 256, sm, h->dc, h->map, h->trav_input, h->normal); break;
   }
   LAUNCH_CHECK();
   return 0;
@@ -363,9 +380,9 @@ int launch_post(emap_handle* h) {
 
 int frame_finish(emap_handle* h) {
   static const int fin_v = getenv("EMAP_FIN_V") ? atoi(getenv("EMAP_FIN_V")) : 1;   // measured on B200: the scalar pass hides the sparse dependent loads best
-  if (h->dc.C % 4 == 0 && fin_v == 4) k_finalize<4><<<cdiv(h->dc.C / 4, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs, h->dc.visibility);
-  else if (h->dc.C % 2 == 0 && fin_v >= 2) k_finalize<2><<<cdiv(h->dc.C / 2, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs, h->dc.visibility);
-  else k_finalize<1><<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map, h->sc, h->fs, h->dc.visibility);
+  if (h->dc.C % 4 == 0 && fin_v == 4) PDL(k_finalize<4>, cdiv(h->dc.C / 4, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility);
+  else if (h->dc.C % 2 == 0 && fin_v >= 2) PDL(k_finalize<2>, cdiv(h->dc.C / 2, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility);
+  else PDL(k_finalize<1>, cdiv(h->dc.C, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility);
   LAUNCH_CHECK();
   if (stage_mark(h, 6)) return EMAP_ERR_CUDA;
   int rc = launch_post(h);

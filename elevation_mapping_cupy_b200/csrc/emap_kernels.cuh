@@ -53,6 +53,12 @@ __device__ __forceinline__ void red_min(u32* p, u32 v, i64 mc) {
   else atomicMin(p, v);
 }
 
+// Programmatic dependent launch (PDL): every frame kernel is launched with programmatic stream serialisation, lets
+// its successor start launching right away (pdl_trigger) and waits for its predecessor's results only where it first
+// needs them (pdl_wait).  With the attribute absent both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- warp aggregation of pushes over RUNS of adjacent lanes that hit the same cell (scan-ordered
 // clouds put consecutive points in the same cell).  Every accumulation is an integer sum / max, so
 // pre-reducing a run in registers and pushing once is exactly equivalent; it is what keeps the number of
@@ -86,6 +92,7 @@ __global__ void __launch_bounds__(256)
 k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64 n, const i64 stride,
               float4* __restrict__ xyzv, int* __restrict__ pidx, const float* __restrict__ map,
               const CellScratch s, FrameScalars* fs, Ray* __restrict__ rays, int* __restrict__ ray_ctl) {
+  pdl_trigger(); pdl_wait();
   const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   i64 e = 0; int ec = 0, nv = 0;
   Ray ray; ray.len = -1.f;
@@ -191,6 +198,7 @@ __global__ void k_set_overlap(FrameScalars* fs, float overlap_tz) {
 // overlap-clear reference is set, and the other half of the double-buffered ray work counters is zeroed.
 __global__ void k_drift(const DevCfg c, FrameScalars* fs, float position_noise, float orientation_noise,
                         float overlap_tz, int set_overlap, int* ray_ctl_next, int n_ctl) {
+  pdl_trigger(); pdl_wait();
   for (int k = threadIdx.x; k < n_ctl; k += blockDim.x) ray_ctl_next[k] = 0;
   if (threadIdx.x || blockIdx.x) return;
   const i64 ecnt = fs->ecnt;
@@ -215,6 +223,7 @@ __global__ void __launch_bounds__(256)
 k_fuse(const DevCfg c, const i64 n, const i64 global_off, const float4* __restrict__ xyzv,
        const int* __restrict__ pidx, const float* __restrict__ map, const CellScratch s,
        const FrameScalars* __restrict__ fs) {
+  pdl_trigger(); pdl_wait();
   const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int idx = -1 - lane;                    // unique negative key: this lane pushes nothing
@@ -302,6 +311,7 @@ __device__ __forceinline__ float add_n_times(float v, float c, u32 n) {
 template <int V>
 __global__ void __launch_bounds__(256)
 k_record(const DevCfg c, const float* __restrict__ map, const CellScratch s, const FrameScalars* __restrict__ fs) {
+  pdl_trigger(); pdl_wait();
   const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (i0 >= c.C) return;
   const size_t C = (size_t)c.C;
@@ -361,8 +371,10 @@ k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __res
   extern __shared__ float s_steps[];             // n_steps padded to a multiple of 32 with +inf
   const int tid = threadIdx.x, lane = tid & 31;
   const int n_pad = (c.n_steps + 31) & ~31;
-  for (int k = tid; k < n_pad; k += RC_THREADS) s_steps[k] = steps[k];
+  pdl_trigger();
+  for (int k = tid; k < n_pad; k += RC_THREADS) s_steps[k] = steps[k];      // static table: before the dependency wait
   __syncthreads();
+  pdl_wait();
   const int n_rays = ray_ctl[0];
   int* next = ray_ctl + 1;
   const int W = c.W, C = c.C;
@@ -452,6 +464,7 @@ k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const F
            const int rays_ran) {
   // V consecutive cells per thread; the dense planes are read as vectors up front, the sparse
   // accumulators (sums, keys) only for the cells that were touched.
+  pdl_trigger(); pdl_wait();
   const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (i0 >= c.C) return;
   const size_t C = (size_t)c.C;
@@ -554,6 +567,7 @@ template <int KT>
 __global__ void __launch_bounds__(256)
 k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, float* __restrict__ normal) {
   extern __shared__ __align__(128) float smem[];
+  pdl_trigger(); pdl_wait();
   const int W = c.W, C = c.C;
   const int K = KT ? KT : c.dilation;
   const int HL = K + 3;                          // row halo of the staged inputs
