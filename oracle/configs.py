@@ -19,6 +19,10 @@ def ref_dict(param: Parameter, min_filter_dilation_size=1):
     return d
 
 
+# parameters under which the drift path (elevation_mapping.py:346-357) triggers with a few thousand points
+DRIFT_OVERRIDES = dict(traversability_inlier=0.0, drift_compensation_variance_inlier=10.0, min_height_drift_cnt=10)
+
+
 def _default202():
     p = Parameter()
     p.update()
@@ -28,6 +32,7 @@ def _default202():
 NAMED_PARAMS = {
     "default202": _default202,                      # dataclass defaults, 8 m / 0.04 m -> 202^2 (reference test shape)
     "core130": lambda: core_parameter(130),         # small map for the committed golden fixtures
+    "drift130": lambda: core_parameter(130, **DRIFT_OVERRIDES),   # drift compensation fires on small test clouds
     "core202": lambda: core_parameter(202),         # deployed core_param.yaml values
     "core256": lambda: core_parameter(256),         # BASELINE config A
     "core512": lambda: core_parameter(512),         # BASELINE config E

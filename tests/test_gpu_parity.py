@@ -299,3 +299,30 @@ def test_device_f64_rows_and_torch_input(oracle_mod):
     om.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
     state, normal = em.get_state()
     compare_state(state, normal, om, label="device f64 rows")
+
+
+def test_drift_compensation_frames_match_oracle(oracle_mod):
+    """the drift path (device-side decision, lazily applied plane shift) with parameters under which it fires"""
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    kw = dict(traversability_inlier=0.0, drift_compensation_variance_inlier=10.0, min_height_drift_cnt=10)
+    p = core_parameter(130, **kw)
+    em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+    fired = 0
+    for f in range(6):
+        pts, R, t = wl.lidar_cloud(0, f, n_rings=24, n_az=500, max_range=4.0)
+        pts = pts.copy(); pts[:, 2] += np.float32(0.03 * (f % 2))
+        for m in (em, om):
+            m.move_to(t, R); m.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+        state, normal = em.get_state()
+        compare_state(state, normal, om, label=f"drift frame {f}")
+        st = em.get_frame_stats()
+        assert st.drift_applied == om.stats.drift_applied and st.error_cnt == om.stats.error_cnt
+        if st.drift_applied:
+            fired += 1
+            assert np.float32(st.mean_error) == np.float32(om.stats.mean_error)
+            assert np.float32(st.shift_applied) == np.float32(om.stats.shift_applied)
+            assert np.float32(st.additive_mean_error) == np.float32(om.additive_mean_error)
+        for m in (em, om):
+            m.update_variance(); m.update_time()
+    assert fired >= 3

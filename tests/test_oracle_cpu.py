@@ -175,3 +175,40 @@ def test_star_plugin_oracles_against_reference_source(oracle_mod):
             assert np.array_equal(ours, out)
         else:       # host build has no FMA contraction: last-ulp differences
             assert np.abs(ours - out).max() <= 5e-7 * max(1.0, np.abs(out).max())
+
+
+def _drift_frames(n=5):
+    out = []
+    for f in range(n):
+        pts, R, t = wl.lidar_cloud(0, f, n_rings=24, n_az=500, max_range=4.0)
+        pts = pts.copy(); pts[:, 2] += np.float32(0.03 * (f % 2))     # alternating 3 cm bias -> non-zero mean error
+        out.append((pts, R, t))
+    return out
+
+
+def test_drift_compensation_against_reference_source(oracle_mod):
+    """EM.py:346-357 fires (error_cnt > min_height_drift_cnt, |mean| < max_drift): oracle vs the reference's kernels"""
+    from oracle.configs import DRIFT_OVERRIDES
+    p = core_parameter(130, **DRIFT_OVERRIDES)
+    try:
+        rf = oracle_mod.RefKernelMap(p, "drift130"); rr = oracle_mod.RefKernelMap(p, "drift130")
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not prebuilt and /root/reference absent")
+    om = oracle_mod.OracleElevationMap(p)
+    fired = 0
+    for pts, R, t in _drift_frames():
+        for m in (rf, rr):
+            m.elevation_map = om.elevation_map.copy(); m.normal_map = om.normal_map.copy(); m.center = om.center.copy()
+            m.additive_mean_error = om.additive_mean_error
+        for m, pp in ((om, pts), (rf, pts), (rr, pts[::-1].copy())):
+            m.move_to(t, R); m.input_pointcloud(pp, ["x", "y", "z"], R, t, 0.02, 0.02)
+        racy = np.zeros((130, 130), bool)
+        for li in (0, 1, 2, 4, 5, 6):
+            racy |= np.abs(rf.elevation_map[li] - rr.elevation_map[li]) > 1e-6
+        for li in (0, 1, 2, 4, 5, 6):
+            assert np.abs(om.elevation_map[li] - rf.elevation_map[li])[~racy].max() <= 1e-6
+        if om.stats.drift_applied:
+            fired += 1
+            assert abs(om.stats.mean_error - float(np.ravel(rf.mean_error)[0])) < 1e-6
+        om.update_variance(); om.update_time()
+    assert fired >= 3
