@@ -379,10 +379,9 @@ int launch_post(emap_handle* h) {
 }
 
 int frame_finish(emap_handle* h) {
-  static const int fin_v = getenv("EMAP_FIN_V") ? atoi(getenv("EMAP_FIN_V")) : 1;   // measured on B200: the scalar pass hides the sparse dependent loads best
-  if (h->dc.C % 4 == 0 && fin_v == 4) PDL(k_finalize<4>, cdiv(h->dc.C / 4, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility);
-  else if (h->dc.C % 2 == 0 && fin_v >= 2) PDL(k_finalize<2>, cdiv(h->dc.C / 2, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility);
-  else PDL(k_finalize<1>, cdiv(h->dc.C, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility);
+  // one cell per thread: measured fastest on B200 (2- and 4-cell vector variants lose more to occupancy -- 96 registers --
+  // than they gain on the dense loads, because the sparse accumulator loads of touched cells are dependent)
+  PDL(k_finalize<1>, cdiv(h->dc.C, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility);
   LAUNCH_CHECK();
   if (stage_mark(h, 6)) return EMAP_ERR_CUDA;
   int rc = launch_post(h);

@@ -160,3 +160,18 @@ def test_sharded_host_logic_gloo_world2(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                        capture_output=True, text=True, env=env, timeout=240)
     assert "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_c_client_compiles_against_the_header(tmp_path):
+    """include/emap.h is plain C: a C99 client (examples/c_api_demo.c) compiles and links against libemap.so."""
+    from elevation_mapping_cupy_b200 import _lib
+    pkg = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "c_api_demo"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "c_api_demo.c"), "-L", pkg, "-lemap", f"-Wl,-rpath,{pkg}",
+                        "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    import shutil
+    if shutil.which("nvidia-smi") is None:          # no GPU here: the client must fail loudly through the error channel
+        assert run.returncode != 0 and "emap_create" in run.stderr
