@@ -683,7 +683,8 @@ k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, 
   // Border columns (cc <= K-2 or cc >= W-K+1): the flat-index window of CK.py:403-407 wraps into the adjacent
   // row there.  Rare (2(K-1) columns of the map), so: one WARP per cell, lanes over the (2K+1)^2 candidates,
   // priority key = (dx+dy, dy) as in the scan of CK.py:429-438, warp-min picks the winner.
-  if (K >= 2 && (c0 - 3 < K - 1 || c0 + PT_X + 3 > W - K)) {
+  if (K >= 2 && (c0 - 3 < K - 1 || c0 + PT_X + 3 > W - K)) {       // block-uniform condition
+    __syncthreads();     // the loop above stored a placeholder for these cells from OTHER threads: order the two writes
     const int lane = tid & 31, warp = tid >> 5, side = 2 * K + 1;
     for (int e = warp; e < DA * DB; e += 8) {
       const int a = e / DB, b = e - a * DB;
