@@ -434,7 +434,7 @@ class RefKernelMap(_MapBase):
         super().__init__(param)
         from . import build_ref
         from .configs import ref_dict
-        self.lib = C.CDLL(build_ref.build(ref_dict(param), tag=tag, gpu=False))
+        self.lib = C.CDLL(build_ref.build(ref_dict(param), tag=tag, gpu=False))      # tag None: named by parameter hash
         assert self.lib.ref_cell_n() == param.cell_n
         W = self.cell_n
         self.new_map = np.zeros((7, W, W), np.float32)

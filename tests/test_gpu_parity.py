@@ -326,3 +326,25 @@ def test_drift_compensation_frames_match_oracle(oracle_mod):
         for m in (em, om):
             m.update_variance(); m.update_time()
     assert fired >= 3
+
+
+@pytest.mark.parametrize("flags", [
+    dict(enable_edge_sharpen=False),
+    dict(enable_visibility_cleanup=False),
+    dict(enable_overlap_clearance=False, enable_drift_compensation=False),
+    dict(max_ray_length=2.0, cleanup_step=0.01, cleanup_cos_thresh=0.5, wall_num_thresh=3, dilation_size=2,
+         min_valid_distance=0.3, mahalanobis_thresh=1.0),
+])
+def test_feature_toggles_match_oracle(oracle_mod, flags):
+    """the same toggles / thresholds tests/test_oracle_cpu.py pins against the reference's kernel source"""
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = core_parameter(130, **flags)
+    em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+    for f in range(3):
+        pts, R, t = wl.lidar_cloud(0, f, n_rings=24, n_az=500, max_range=4.0)
+        for m in (em, om):
+            m.move_to(t, R); m.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+            m.update_variance(); m.update_time()
+        state, normal = em.get_state()
+        compare_state(state, normal, om, label=f"{flags} frame {f}")

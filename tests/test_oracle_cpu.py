@@ -212,3 +212,41 @@ def test_drift_compensation_against_reference_source(oracle_mod):
             assert abs(om.stats.mean_error - float(np.ravel(rf.mean_error)[0])) < 1e-6
         om.update_variance(); om.update_time()
     assert fired >= 3
+
+
+@pytest.mark.parametrize("flags", [
+    dict(enable_edge_sharpen=False),
+    dict(enable_visibility_cleanup=False),
+    dict(enable_overlap_clearance=False, enable_drift_compensation=False),
+    dict(max_ray_length=2.0, cleanup_step=0.01, cleanup_cos_thresh=0.5, wall_num_thresh=3, dilation_size=2,
+         min_valid_distance=0.3, mahalanobis_thresh=1.0),
+])
+def test_flag_combinations_against_reference_source(oracle_mod, flags):
+    """feature toggles and thresholds are baked into the reference's kernel source: build it per combination
+    (needs /root/reference) and compare three frames on the order-independent cells"""
+    from oracle import build_ref
+    from oracle.configs import ref_dict
+    if not os.path.isdir(build_ref.REF_ROOT):
+        pytest.skip("/root/reference absent")
+    p = core_parameter(130, **flags)
+    om = oracle_mod.OracleElevationMap(p)
+    for f in range(3):
+        pts, R, t = wl.lidar_cloud(0, f, n_rings=24, n_az=500, max_range=4.0)
+        refs = []
+        for order in (1, -1):
+            rm = oracle_mod.RefKernelMap(p, None)
+            rm.elevation_map = om.elevation_map.copy(); rm.normal_map = om.normal_map.copy(); rm.center = om.center.copy()
+            rm.additive_mean_error = om.additive_mean_error
+            rm.move_to(t, R); rm.input_pointcloud(pts[::order].copy(), ["x", "y", "z"], R, t, 0.02, 0.02)
+            refs.append(rm)
+        om.move_to(t, R); om.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+        racy = np.zeros((130, 130), bool)
+        for li in (0, 1, 2, 4, 5, 6):
+            racy |= np.abs(refs[0].elevation_map[li] - refs[1].elevation_map[li]) > 1e-6
+        n_cmp = int((~racy).sum())
+        for li in (0, 1, 2, 4, 5, 6):
+            d = np.abs(om.elevation_map[li] - refs[0].elevation_map[li])[~racy]
+            assert int((d > 1e-6).sum()) <= 3, (flags, f, li, float(d.max()))      # symmetric order-dependent patterns
+        assert np.array_equal(om.last_point_record[0], refs[0].last_point_record[0])
+        assert n_cmp > 0.9 * 130 * 130
+        om.update_variance(); om.update_time()
