@@ -213,7 +213,7 @@ def build(P, tag=None, gpu=False, verbose=False):
                "-DREF_SHIM_GPU", "-I", HERE, "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared",
                "-o", so, src_path]
     else:
-        cmd = ["g++", "-O2", "-std=c++17", "-march=native", "-ffp-contract=off", "-fopenmp", "-w", "-I", HERE,
+        cmd = ["g++", "-O2", "-std=c++17", "-march=x86-64-v3", "-ffp-contract=off", "-fopenmp", "-w", "-I", HERE,
                "-shared", "-fPIC", "-o", so, src_path]
     if verbose:
         print(" ".join(cmd))
