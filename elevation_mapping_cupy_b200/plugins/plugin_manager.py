@@ -1,16 +1,18 @@
-"""Plugin layer API -- mirror of the reference's plugin manager
-(elevation_mapping_cupy/script/elevation_mapping_cupy/plugins/plugin_manager.py:15-235):
-same `PluginParams`, `PluginBase.__call__` signature, YAML schema (`enable, fill_nan,
-is_height_layer, layer_name, type?, extra_params`, :134-151), `cell_n` injection (:128) and
-arity-based dispatch (:193-225).  Layers are torch CUDA tensors instead of CuPy arrays; PyYAML
-replaces ruamel.  The built-in plugins run libemap.so kernels through the `engine` handle the
-manager passes to their constructors (user plugins may ignore it: every reference plugin takes **kwargs).
+"""Plugin layer API of the drop-in.
+
+Contract taken from the reference's plugin manager
+(elevation_mapping_cupy/script/elevation_mapping_cupy/plugins/plugin_manager.py): the names `PluginParams`,
+`PluginBase`, `PluginManager` and their public methods (:15-20, :23-108, :111-235), the YAML schema
+(`enable, fill_nan, is_height_layer, layer_name, type?, extra_params`, :134-151), the injection of `cell_n` into the
+plugin constructor (:128) and the dispatch on the ARITY of a plugin's `__call__` (:193-225: 5, 7, 8 parameters, else
+all of them).  Differences: layers are torch CUDA tensors (they expose `__cuda_array_interface__`), the YAML is read
+with PyYAML, and the manager hands its `engine` (the owning ElevationMap) to plugin constructors so that the built-in
+plugins can run libemap.so kernels -- user plugins simply swallow it in **kwargs like every reference plugin does.
 """
 from abc import ABC
 from dataclasses import dataclass
 import importlib
 import inspect
-from inspect import signature
 from typing import Dict, List, Optional
 
 import yaml
@@ -18,130 +20,121 @@ import yaml
 
 @dataclass
 class PluginParams:
-    name: str
-    layer_name: str
-    fill_nan: bool = False        # fill nan to invalid region
-    is_height_layer: bool = False  # if this is a height layer
+    name: str                      # module (file) name of the plugin
+    layer_name: str                # name of the layer it produces
+    fill_nan: bool = False         # export: NaN where the elevation cell is not valid
+    is_height_layer: bool = False  # export: add the map centre height
 
 
 class PluginBase(ABC):
-    """Base class of plugins (plugin_manager.py:23-108)."""
+    """Base class: subclass it in a module of the plugin package and implement `__call__`.
+
+    `__call__(elevation_map, layer_names, plugin_layers, plugin_layer_names[, semantic_map, semantic_layer_names
+    [, rotation[, elements_to_shift]]])` returns one `(cell_n, cell_n)` device array.  Layer order of
+    `elevation_map`: elevation, variance, is_valid, traversability, time, upper_bound, is_upper_bound.
+    """
 
     def __init__(self, *args, **kwargs):
         pass
 
     def __call__(self, elevation_map, layer_names: List[str], plugin_layers, plugin_layer_names: List[str],
                  semantic_map=None, semantic_layer_names: List[str] = None, *args, **kwargs):
-        """elevation_map layers: 0 elevation, 1 variance, 2 is_valid, 3 traversability, 4 time,
-        5 upper_bound, 6 is_upper_bound.  Return a (cell_n, cell_n) device array."""
-        pass
+        return None
 
     def get_layer_data(self, elevation_map, layer_names, plugin_layers, plugin_layer_names, semantic_map,
                        semantic_layer_names, name) -> Optional[object]:
-        """plugin_manager.py:71-108: a copy of the named layer, or None."""
-        if name in layer_names:
-            return elevation_map[layer_names.index(name)].clone()
-        if name in plugin_layer_names:
-            return plugin_layers[plugin_layer_names.index(name)].clone()
-        if semantic_layer_names and name in semantic_layer_names:
-            return semantic_map[semantic_layer_names.index(name)].clone()
+        """A private copy of the layer called `name`, searched in the map, the plugin layers, then the semantic layers."""
+        for names, store in ((layer_names, elevation_map), (plugin_layer_names, plugin_layers),
+                             (semantic_layer_names or [], semantic_map)):
+            if name in names:
+                return store[names.index(name)].clone()
         print(f"Could not find layer {name}!")
         return None
 
 
 class PluginManager(object):
-    """Manages the plugins (plugin_manager.py:111-235)."""
-
     def __init__(self, cell_n: int, engine=None, package: str = "elevation_mapping_cupy_b200.plugins"):
         self.cell_n = cell_n
         self.engine = engine
         self.package = package
         self.plugin_params: List[PluginParams] = []
-        self.plugins = []
-        self.layers = None
+        self.plugins: list = []
+        self.layers = None                 # (n_plugins, cell_n, cell_n) fp32, allocated on first use
         self.layer_names: List[str] = []
         self.plugin_names: List[str] = []
 
+    # ---- construction ------------------------------------------------------------------------
     def init(self, plugin_params: List[PluginParams], extra_params: List[Dict]):
-        self.plugin_params = plugin_params
+        self.plugin_params = list(plugin_params)
         self.plugins = []
-        for param, extra_param in zip(plugin_params, extra_params):
-            m = importlib.import_module("." + param.name, package=self.package)
-            for name, obj in inspect.getmembers(m):
-                if inspect.isclass(obj) and issubclass(obj, PluginBase) and name != "PluginBase":
-                    extra_param = dict(extra_param or {})
-                    extra_param["cell_n"] = self.cell_n          # plugin_manager.py:128
-                    extra_param["engine"] = self.engine
-                    self.plugins.append(obj(**extra_param))
-        self.layers = None                                        # allocated lazily on the engine's device
+        for spec, extra in zip(plugin_params, extra_params):
+            module = importlib.import_module("." + spec.name, package=self.package)
+            kwargs = dict(extra or {}, cell_n=self.cell_n, engine=self.engine)
+            for cls_name, cls in inspect.getmembers(module, inspect.isclass):
+                if cls_name != "PluginBase" and issubclass(cls, PluginBase):
+                    self.plugins.append(cls(**kwargs))
+        self.layers = None
         self.layer_names = self.get_layer_names()
         self.plugin_names = self.get_plugin_names()
 
-    def _ensure_layers(self, like):
+    def load_plugin_settings(self, file_path: str):
+        print("Start loading plugins...")
+        with open(file_path, "r") as stream:
+            entries = yaml.safe_load(stream) or {}
+        specs, extras = [], []
+        for key, entry in entries.items():
+            if not entry["enable"]:
+                continue
+            specs.append(PluginParams(name=entry.get("type", key), layer_name=entry["layer_name"],
+                                      fill_nan=entry["fill_nan"], is_height_layer=entry["is_height_layer"]))
+            extras.append(entry.get("extra_params", {}))
+        self.init(specs, extras)
+        print("Loaded plugins are ", *self.plugin_names)
+
+    # ---- look-ups ----------------------------------------------------------------------------
+    def get_layer_names(self):
+        return [spec.layer_name for spec in self.plugin_params]
+
+    def get_plugin_names(self):
+        return [spec.name for spec in self.plugin_params]
+
+    def get_plugin_index_with_name(self, name: str) -> Optional[int]:
+        if name in self.plugin_names:
+            return self.plugin_names.index(name)
+        print("Error with plugin {}: not loaded".format(name))
+        return None
+
+    def get_layer_index_with_name(self, name: str) -> Optional[int]:
+        if name in self.layer_names:
+            return self.layer_names.index(name)
+        print("Error with layer {}: not a plugin layer".format(name))
+        return None
+
+    def get_map_with_name(self, name: str):
+        idx = self.get_layer_index_with_name(name)
+        return None if idx is None or self.layers is None else self.layers[idx]
+
+    def get_param_with_name(self, name: str) -> Optional[PluginParams]:
+        idx = self.get_layer_index_with_name(name)
+        return None if idx is None else self.plugin_params[idx]
+
+    # ---- evaluation --------------------------------------------------------------------------
+    def _storage(self, like):
         if self.layers is None:
             import torch
             self.layers = torch.zeros((len(self.plugins), self.cell_n, self.cell_n), dtype=torch.float32,
                                       device=like.device)
-
-    def load_plugin_settings(self, file_path: str):
-        print("Start loading plugins...")
-        with open(file_path, "r") as f:
-            cfg = yaml.safe_load(f) or {}
-        plugin_params, extra_params = [], []
-        for k, v in cfg.items():
-            if v["enable"]:
-                plugin_params.append(PluginParams(name=k if "type" not in v else v["type"], layer_name=v["layer_name"],
-                                                  fill_nan=v["fill_nan"], is_height_layer=v["is_height_layer"]))
-                extra_params.append(v.get("extra_params", {}))
-        self.init(plugin_params, extra_params)
-        print("Loaded plugins are ", *self.plugin_names)
-
-    def get_layer_names(self):
-        return [obj.layer_name for obj in self.plugin_params]
-
-    def get_plugin_names(self):
-        return [obj.name for obj in self.plugin_params]
-
-    def get_plugin_index_with_name(self, name: str) -> int:
-        try:
-            return self.plugin_names.index(name)
-        except Exception as e:
-            print("Error with plugin {}: {}".format(name, e))
-            return None
-
-    def get_layer_index_with_name(self, name: str) -> int:
-        try:
-            return self.layer_names.index(name)
-        except Exception as e:
-            print("Error with layer {}: {}".format(name, e))
-            return None
+        return self.layers
 
     def update_with_name(self, name: str, elevation_map, layer_names: List[str], semantic_map=None,
                          semantic_params=None, rotation=None, elements_to_shift={}):
-        """plugin_manager.py:181-225: dispatch by the number of parameters of the plugin's __call__."""
+        """Recompute the plugin layer `name`.  How many optional arguments the plugin receives depends on how many
+        parameters its `__call__` declares (plugin_manager.py:193-225 of the reference)."""
         idx = self.get_layer_index_with_name(name)
-        if idx is not None and idx < len(self.plugins):
-            self._ensure_layers(elevation_map)
-            n_param = len(signature(self.plugins[idx]).parameters)
-            if n_param == 5:
-                out = self.plugins[idx](elevation_map, layer_names, self.layers, self.layer_names)
-            elif n_param == 7:
-                out = self.plugins[idx](elevation_map, layer_names, self.layers, self.layer_names, semantic_map,
-                                        semantic_params)
-            elif n_param == 8:
-                out = self.plugins[idx](elevation_map, layer_names, self.layers, self.layer_names, semantic_map,
-                                        semantic_params, rotation)
-            else:
-                out = self.plugins[idx](elevation_map, layer_names, self.layers, self.layer_names, semantic_map,
-                                        semantic_params, rotation, elements_to_shift)
-            self.layers[idx] = out
-
-    def get_map_with_name(self, name: str):
-        idx = self.get_layer_index_with_name(name)
-        if idx is not None:
-            return self.layers[idx]
-
-    def get_param_with_name(self, name: str) -> PluginParams:
-        idx = self.get_layer_index_with_name(name)
-        if idx is not None:
-            return self.plugin_params[idx]
+        if idx is None or idx >= len(self.plugins):
+            return
+        layers = self._storage(elevation_map)
+        plugin = self.plugins[idx]
+        optional = (semantic_map, semantic_params, rotation, elements_to_shift)
+        n_optional = {5: 0, 7: 2, 8: 3}.get(len(inspect.signature(plugin).parameters), 4)
+        layers[idx] = plugin(elevation_map, layer_names, layers, self.layer_names, *optional[:n_optional])

@@ -1,6 +1,10 @@
-"""smooth_filter plugin: two passes of a 3x3 uniform filter with reflect borders
-(reference: elevation_mapping_cupy/script/elevation_mapping_cupy/plugins/smooth_filter.py:12-59,
-which calls cupyx.scipy.ndimage.uniform_filter twice).  Runs in libemap.so (`emap_smooth_filter`)."""
+"""smooth_filter plugin: the chosen layer passed twice through a 3x3 mean with mirrored borders.
+
+The reference (elevation_mapping_cupy/script/elevation_mapping_cupy/plugins/smooth_filter.py:12-59) calls
+cupyx.scipy.ndimage.uniform_filter(size=3) two times; here the four 1-D passes run in libemap.so
+(`emap_smooth_filter`) with the same double-precision accumulation per pass.  Falls back to the elevation
+layer, with the reference's message, when `input_layer_name` is unknown.
+"""
 from typing import List
 
 from .plugin_manager import PluginBase
@@ -13,19 +17,20 @@ class SmoothFilter(PluginBase):
         self.input_layer_name = input_layer_name
         self.engine = engine
 
+    def _source(self, elevation_map, layer_names, plugin_layers, plugin_layer_names):
+        want = self.input_layer_name
+        for names, store in ((layer_names, elevation_map), (plugin_layer_names, plugin_layers)):
+            if want in names:
+                return store[names.index(want)]
+        print("layer name {} was not found. Using elevation layer.".format(want))
+        return elevation_map[0]
+
     def __call__(self, elevation_map, layer_names: List[str], plugin_layers, plugin_layer_names: List[str], *args):
         import torch
         eng = require_engine(self.engine, "SmoothFilter")
-        if self.input_layer_name in layer_names:
-            h = elevation_map[layer_names.index(self.input_layer_name)]
-        elif self.input_layer_name in plugin_layer_names:
-            h = plugin_layers[plugin_layer_names.index(self.input_layer_name)]
-        else:
-            print("layer name {} was not found. Using elevation layer.".format(self.input_layer_name))
-            h = elevation_map[0]
-        h = as_plane(h)
-        out = torch.empty_like(h)
+        src = as_plane(self._source(elevation_map, layer_names, plugin_layers, plugin_layer_names))
+        dst = torch.empty_like(src)
         sync_in()
-        eng._check(eng._L.emap_smooth_filter(eng._h, h.data_ptr(), out.data_ptr()))
+        eng._check(eng._L.emap_smooth_filter(eng._h, src.data_ptr(), dst.data_ptr()))
         eng.synchronize()
-        return out
+        return dst
