@@ -27,6 +27,14 @@
  *     the reference source compiled by oracle/build_ref.py).
  * Build with -ffp-contract=off so that nothing else is contracted.
  *
+ * Parity pinning.  PINNED against the reference's own kernel source: oracle/build_ref.py compiles the CUDA-C strings
+ * of kernels/custom_kernels.py and plugins/{min,max}_filter.py, robot_centric_elevation.py unmodified for the host
+ * (and for sm_100a); tests/test_oracle_cpu.py compares this file with that build (live, and through the committed
+ * golden vectors of tests/golden/): bit-identical cell indices, <= 1e-6 on every order-independent cell, for the
+ * deployed parameters, the dataclass defaults and four toggle / threshold combinations.  Restated rather than
+ * executed (third party, absent here): CuPy's `class float16` (oracle/ref_shim.h), cuDNN's convolution order,
+ * cupyx's uniform_filter -- see DESIGN.md section 2.
+ *
  * Serialisation.  The reference kernel is racy by construction.
  * This oracle executes the CANONICAL SERIALISATION of SURVEY 8(c): a legal
  * interleaving of the reference kernel in which (1) the error-count pass runs,
