@@ -77,6 +77,7 @@ SIGNATURES = {
     "emap_robot_centric_elevation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_double, C.c_double, C.c_int32]),
     "emap_inpaint": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "emap_inpaint_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "emap_sync": (C.c_int, [C.c_void_p]),
     "emap_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "emap_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -10,6 +10,7 @@
 
 #include "../../include/emap.h"
 #include "emap_kernels.cuh"
+#include "emap_inpaint.cuh"
 
 namespace {
 
@@ -28,7 +29,8 @@ struct emap_handle {
   int device = 0;
   std::mutex mu;
   std::string err;
-  cudaStream_t stream = nullptr, copy_stream = nullptr, own_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, own_stream = nullptr, side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;     // side-stream fork / join of the deferred fusion pushes
   // state
   float* map = nullptr;       // (7,W,W)
   float* map_alt = nullptr;   // shift target
@@ -38,12 +40,19 @@ struct emap_handle {
   float base_rotation[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   // scratch
   CellScratch sc{};
-  u32* u32_block = nullptr;   // cnt_all | cnt_inl | cnt_fused | n_out | n_ray
+  u32* u32_block = nullptr;   // cnt_ai (2 x u32 per cell) | cnt_fo (2 x u32 per cell) | n_ray
   i64* i64_block = nullptr;   // SH | SV | DV
   int* ukey_x = nullptr;      // exchange copy of the upper-bound keys (sharded frames)
   FrameScalars* fs = nullptr;
-  float* steps = nullptr;     // device copy of the march table
+  float* steps = nullptr;     // device march table: [0] dummy, [1 + k] = s_k, +inf padded to n_tab entries
+  int n_tab = 0;
   std::vector<float> steps_host;
+  unsigned short* lut = nullptr;   // cell of every fp16 bit pattern (k_build_lut)
+  unsigned char* dirty = nullptr;  // per-cell dirty bytes of single-GPU frames (CellScratch::dirty)
+  u32* tmap = nullptr;             // coarse ray map of the frame: RT x RT tile maxima of thr (keys)
+  size_t rc_smem = 0;
+  RcLayout rc_lay{};
+  int span_cells = 0;              // cells (per axis) one 31-step warp iteration of the march can span
   // points
   void* d_in[2] = {nullptr, nullptr};
   size_t d_in_bytes[2] = {0, 0};
@@ -52,9 +61,8 @@ struct emap_handle {
   float4* xyzv = nullptr;
   int* pidx = nullptr;
   Ray* rays = nullptr;        // compacted rays of the frame, one segment per sensor (at the sensor's point offset)
-  int* ray_ctl = nullptr;     // per sensor: {ray count, work counter}; two halves used by alternate frames
-  int ray_ctl_cap = 0;        // sensors per half
-  int ray_sel = 0;            // half used by the current frame
+  int* ray_ctl = nullptr;     // per sensor: {ray count, work counter}; zero between frames (k_finalize)
+  int ray_ctl_cap = 0;        // sensors
   bool overlap_override = false;
   float overlap_z_override = 0.f;
   i64 pt_cap = 0;
@@ -78,6 +86,10 @@ struct emap_handle {
   float* pl[4] = {nullptr, nullptr, nullptr, nullptr};
   int* pl_cnt = nullptr;
   int pl_cnt_cap = 0;
+  // inpainting scratch (allocated on first use): one block, carved into the arrays of InpaintView + lists + control
+  void* ip_block = nullptr;
+  size_t ip_bytes = 0;
+  int ip_grid = 0;
   // misc
   int64_t launches = 0;
   int count_rays = 0;
@@ -164,6 +176,16 @@ void fill_devcfg(const emap_config& c, DevCfg& d) {
   d.res_f = (float)c.resolution;
   d.overlap_z_f = (float)c.overlap_clear_range_z; d.time_var_f = (float)c.time_variance;
   d.time_int_f = (float)c.time_interval;
+  // ray-march cell table: fp16 coordinates are clamped to [-LIM, LIM], LIM = the first fp16 value >= (W/2 + 1) * resolution;
+  // every value at or beyond +-LIM maps to cell W-1 / 0, so only the bit patterns [0, P) and [0x8000, 0x8000 + P) are staged
+  {
+    const double want = (0.5 * (double)c.cell_n + 1.0) * c.resolution;
+    __half hl = __float2half_ru((float)std::min(want, 60000.0));
+    unsigned short bits = __half_as_ushort(hl);
+    if (bits > 0x7bff) bits = 0x7bff;
+    d.lut_lim2 = ((u32)bits << 16) | bits;
+    d.lut_p2 = (int)(((size_t)(bits + 1) * 2 + 15) & ~(size_t)15);
+  }
 }
 
 // CK.py:203,268: the fp16 march variable, identical for every ray
@@ -171,7 +193,7 @@ void build_steps(const emap_config& c, float max_len16, std::vector<float>& out)
   const double ray_step = c.resolution / std::sqrt(2.0);
   out.clear();
   float s = h16_host((float)ray_step);
-  while (s < max_len16 && out.size() < 65536) {
+  while (s < max_len16 && out.size() < 65535) {
     out.push_back(s);
     float nx = h16_host((float)((double)s + ray_step));
     if (!(nx > s)) break;      // fp16 spacing exceeded the step: the reference would spin forever
@@ -216,14 +238,16 @@ template <typename T>
 int launch_index(emap_handle* h, const Pose& q, const T* pts, i64 n, i64 stride, i64 off, int sensor) {
   if (n <= 0) return 0;
   PDL(k_index_error<T>, cdiv(n, 256), 256, 0, h->dc, q, pts, n, stride, h->xyzv + off, h->pidx + off, (const float*)h->map,
-      h->sc, h->fs, h->rays + off, h->ray_ctl + 2 * (h->ray_sel * h->ray_ctl_cap + sensor));
+      h->sc, h->fs, h->rays + off, h->ray_ctl + 2 * sensor, (const float*)(h->steps + 1));
   LAUNCH_CHECK();
   return 0;
 }
 
 // phase 0: upload + index/error pass for every sensor
 int frame_begin(emap_handle* h, int32_t n_sensors, const void* const* points, const int64_t* n, int64_t row_stride,
-                int dtype, int is_device_ptr, const float* R, const float* t, int64_t global_off, float pn, float on) {
+                int dtype, int is_device_ptr, const float* R, const float* t, int64_t global_off, float pn, float on,
+                bool sharded) {
+  h->sc.dirty = sharded ? nullptr : h->dirty;      // sharded frames derive the marker from the all-reduced counts
   if (n_sensors < 1 || row_stride < 3 || (dtype != EMAP_F32 && dtype != EMAP_F64))
     return fail(h, EMAP_ERR_INVALID, "emap_input: n_sensors >= 1, row_stride >= 3, dtype f32/f64 required");
   const size_t esz = dtype == EMAP_F32 ? 4 : 8;
@@ -248,11 +272,10 @@ int frame_begin(emap_handle* h, int32_t n_sensors, const void* const* points, co
     CK(cudaStreamSynchronize(h->stream));
     if (h->ray_ctl) cudaFree(h->ray_ctl);
     h->ray_ctl = nullptr; h->ray_ctl_cap = 0;
-    CK(cudaMalloc(&h->ray_ctl, sizeof(int) * 4 * (n_sensors + 8)));
-    CK(cudaMemset(h->ray_ctl, 0, sizeof(int) * 4 * (n_sensors + 8)));
+    CK(cudaMalloc(&h->ray_ctl, sizeof(int) * 2 * (n_sensors + 8)));
+    CK(cudaMemsetAsync(h->ray_ctl, 0, sizeof(int) * 2 * (n_sensors + 8), h->stream));   // ordered before the frame's kernels
     h->ray_ctl_cap = n_sensors + 8;
   }
-  h->ray_sel ^= 1;                                 // this half was zeroed by the previous frame's k_drift
   h->overlap_override = false;
   if (stage_mark(h, 0)) return EMAP_ERR_CUDA;
   const void* dev_pts[64];
@@ -318,14 +341,20 @@ int frame_index(emap_handle* h) {
 }
 
 int frame_fuse(emap_handle* h) {
-  PDL(k_drift, 1, 32, 0, h->dc, h->fs, h->pos_noise, h->ori_noise,
-      h->overlap_override ? h->overlap_z_override : h->poses[0].t[2], 1,
-      h->ray_ctl + 2 * ((h->ray_sel ^ 1) * h->ray_ctl_cap), 2 * h->ray_ctl_cap);
+  PDL(k_drift, 1, 256, 0, h->dc, h->fs, h->pos_noise, h->ori_noise,
+      h->overlap_override ? h->overlap_z_override : h->poses[0].t[2], 1, h->tmap);
   LAUNCH_CHECK();
   if (stage_mark(h, 2)) return EMAP_ERR_CUDA;
   if (h->n_points > 0) {
-    PDL(k_fuse, cdiv(h->n_points, 256), 256, 0, h->dc, h->n_points, h->global_off, (const float4*)h->xyzv,
-        (const int*)h->pidx, (const float*)h->map, h->sc, (const FrameScalars*)h->fs);
+    if (h->attached) {
+      // NVLink multicast: only the counts are on the critical path; sums + last-writer keys follow on the side stream
+      // (frame_rays), under the ray-cast
+      PDL(k_fuse<1>, cdiv(h->n_points, 256), 256, 0, h->dc, h->n_points, h->global_off, (const float4*)h->xyzv,
+          (const int*)h->pidx, (const float*)h->map, h->sc, (const FrameScalars*)h->fs);
+    } else {
+      PDL(k_fuse<3>, cdiv(h->n_points, 256), 256, 0, h->dc, h->n_points, h->global_off, (const float4*)h->xyzv,
+          (const int*)h->pidx, (const float*)h->map, h->sc, (const FrameScalars*)h->fs);
+    }
     LAUNCH_CHECK();
   }
   if (stage_mark(h, 3)) return EMAP_ERR_CUDA;
@@ -333,27 +362,72 @@ int frame_fuse(emap_handle* h) {
   return 0;
 }
 
+// Cells a ray of this frame can reach.  A sample is t + ray*s with |ray| <= 1 per axis and s < len <= max_len16, so it
+// lies within max_len16 of the sensor on each axis; its fp16 rounding moves it by at most 2^-11 of its magnitude.
+// Rows [r0, r1) x columns [c0, c1), columns aligned to `align`; union over the frame's sensors, two cells of slack.
+// Tile size 2^ts: at most RT tiles per axis, and a double-size tile at least half the span of one warp iteration
+// (so that an iteration starting anywhere in a double tile stays inside the 3 x 3 block k_raycast tests).
+RayGrid ray_grid(const emap_handle* h, int align) {
+  const int W = h->dc.W;
+  int r0 = W, r1 = 0, c0 = W, c1 = 0;
+  const double L = (double)h->dc.max_len16;
+  for (const Pose& q : h->poses) {
+    for (int ax = 0; ax < 2; ax++) {
+      const double tc = (double)q.t[ax];
+      const double e = (std::fabs(tc) + L) * (1.0 / 2048.0) + 1e-4;
+      double lo = std::floor((tc - L - e) / h->dc.resolution + h->dc.half_w) - 2.0;
+      double hi = std::floor((tc + L + e) / h->dc.resolution + h->dc.half_w) + 3.0;
+      if (!(lo == lo) || !(hi == hi)) { lo = 0; hi = W; }         // NaN pose: whole map
+      const int a = (int)std::min(std::max(lo, 0.0), (double)W), b = (int)std::min(std::max(hi, 0.0), (double)W);
+      if (ax == 0) { r0 = std::min(r0, a); r1 = std::max(r1, b); } else { c0 = std::min(c0, a); c1 = std::max(c1, b); }
+    }
+  }
+  RayGrid g{0, 0, 0, 0, 3};
+  if (r1 <= r0 || c1 <= c0) return g;
+  c0 = (c0 / align) * align; c1 = std::min(W, ((c1 + align - 1) / align) * align);
+  g.r0 = r0; g.r1 = r1; g.c0 = c0; g.c1 = c1;
+  int ts = 2;
+  while ((RT << ts) < std::max(r1 - r0, c1 - c0) || (4 << ts) < h->span_cells + 1) ts++;
+  g.ts = ts;
+  return g;
+}
+
 int frame_rays(emap_handle* h) {
-  if (h->dc.visibility) {
-    if (h->dc.C % 4 == 0) PDL(k_record<4>, cdiv(h->dc.C / 4, 256), 256, 0, h->dc, (const float*)h->map, h->sc, (const FrameScalars*)h->fs);
-    else PDL(k_record<1>, cdiv(h->dc.C, 256), 256, 0, h->dc, (const float*)h->map, h->sc, (const FrameScalars*)h->fs);
+  const bool deferred = h->attached && h->n_points > 0;
+  if (deferred) {   // sums + last-writer keys of the fusion: multicast pushes on the side stream, under the ray-cast
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    k_fuse<2><<<cdiv(h->n_points, 256), 256, 0, h->side_stream>>>(h->dc, h->n_points, h->global_off, (const float4*)h->xyzv,
+                                                                    (const int*)h->pidx, (const float*)h->map, h->sc,
+                                                                    (const FrameScalars*)h->fs);
     LAUNCH_CHECK();
+    CK(cudaEventRecord(h->ev_join, h->side_stream));
+  }
+  if (h->dc.visibility) {
+    const int V = (h->dc.W % 4 == 0) ? 4 : 1;
+    const RayGrid box = ray_grid(h, V);
+    const i64 nthreads = (i64)(box.r1 - box.r0) * ((box.c1 - box.c0) / V);
+    if (nthreads > 0) {
+      if (V == 4) PDL(k_record<4>, cdiv(nthreads, 256), 256, 0, h->dc, (const float*)h->map, h->sc, (const FrameScalars*)h->fs, box, h->tmap);
+      else PDL(k_record<1>, cdiv(nthreads, 256), 256, 0, h->dc, (const float*)h->map, h->sc, (const FrameScalars*)h->fs, box, h->tmap);
+      LAUNCH_CHECK();
+    }
     if (stage_mark(h, 4)) return EMAP_ERR_CUDA;
-    const size_t sm = sizeof(float) * (size_t)((h->dc.n_steps + 31) & ~31);
     for (size_t s = 0; s + 1 < h->offs.size(); s++) {
       const i64 n = h->offs[s + 1] - h->offs[s];
       if (n <= 0 || h->dc.n_steps == 0) continue;
       // persistent grid: enough CTAs to fill every SM, never more than one warp per possible ray
-      const int grid = (int)std::min<i64>((i64)h->n_sm * h->rc_blocks_per_sm, (n + 3) / 4);
+      const int grid = (int)std::min<i64>((i64)h->n_sm * h->rc_blocks_per_sm, (n + RC_THREADS / 32 - 1) / (RC_THREADS / 32));
       if (h->count_rays)
-        PDL(k_raycast<true>, grid, RC_THREADS, sm, h->dc, h->poses[s], (const Ray*)(h->rays + h->offs[s]), h->ray_ctl + 2 * (h->ray_sel * h->ray_ctl_cap + (int)s),
-            (const float*)h->map, (const float*)h->normal, h->sc, (const float*)h->steps, h->fs);
+        PDL(k_raycast<true>, grid, RC_THREADS, h->rc_smem, h->dc, h->poses[s], (const Ray*)(h->rays + h->offs[s]), h->ray_ctl + 2 * (int)s,
+            (const float*)h->map, (const float*)h->normal, h->sc, (const float*)h->steps, h->n_tab, (const unsigned short*)h->lut, box, (const u32*)h->tmap, h->rc_lay, h->fs);
       else
-        PDL(k_raycast<false>, grid, RC_THREADS, sm, h->dc, h->poses[s], (const Ray*)(h->rays + h->offs[s]), h->ray_ctl + 2 * (h->ray_sel * h->ray_ctl_cap + (int)s),
-            (const float*)h->map, (const float*)h->normal, h->sc, (const float*)h->steps, h->fs);
+        PDL(k_raycast<false>, grid, RC_THREADS, h->rc_smem, h->dc, h->poses[s], (const Ray*)(h->rays + h->offs[s]), h->ray_ctl + 2 * (int)s,
+            (const float*)h->map, (const float*)h->normal, h->sc, (const float*)h->steps, h->n_tab, (const unsigned short*)h->lut, box, (const u32*)h->tmap, h->rc_lay, h->fs);
       LAUNCH_CHECK();
     }
   } else if (stage_mark(h, 4)) return EMAP_ERR_CUDA;
+  if (deferred) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));   // before the cross-rank barrier that follows this phase
   if (stage_mark(h, 5)) return EMAP_ERR_CUDA;
   h->phase = 3;
   return 0;
@@ -379,9 +453,8 @@ int launch_post(emap_handle* h) {
 }
 
 int frame_finish(emap_handle* h) {
-  // one cell per thread: measured fastest on B200 (2- and 4-cell vector variants lose more to occupancy -- 96 registers --
-  // than they gain on the dense loads, because the sparse accumulator loads of touched cells are dependent)
-  PDL(k_finalize<1>, cdiv(h->dc.C, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility);
+  if (h->dc.W % 4 == 0) PDL(k_finalize<4>, cdiv(h->dc.C / 4, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility, h->ray_ctl, 2 * h->ray_ctl_cap);
+  else PDL(k_finalize<1>, cdiv(h->dc.C, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility, h->ray_ctl, 2 * h->ray_ctl_cap);
   LAUNCH_CHECK();
   if (stage_mark(h, 6)) return EMAP_ERR_CUDA;
   int rc = launch_post(h);
@@ -403,19 +476,16 @@ int alloc_plugin_scratch(emap_handle* h) {
   return 0;
 }
 
-// upper-bound keys of a sharded frame: invalid cells carry theirs in rec.x, valid cells in ukv
-__global__ void k_ukey_extract(int C, const uint2* __restrict__ rec, const u32* __restrict__ ukv, int* __restrict__ x) {
+// upper-bound keys of a sharded frame (NCCL mode): u32 keys <-> the s32 order an int32 MIN all-reduce needs
+__global__ void k_ukey_extract(int C, const u32* __restrict__ ukv, int* __restrict__ x) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C) return;
-  const uint2 r = rec[i];
-  const u32 k = (r.y & RF_VALID) ? ukv[i] : r.x;
-  x[i] = (int)(k ^ 0x80000000u);                         // order-preserving u32 -> s32
+  x[i] = (int)(ukv[i] ^ 0x80000000u);                    // order-preserving u32 -> s32
 }
-__global__ void k_ukey_merge(int C, uint2* __restrict__ rec, u32* __restrict__ ukv, const int* __restrict__ x) {
+__global__ void k_ukey_merge(int C, u32* __restrict__ ukv, const int* __restrict__ x) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C) return;
-  const u32 k = ((u32)x[i]) ^ 0x80000000u;
-  if (rec[i].y & RF_VALID) ukv[i] = k; else rec[i].x = k;
+  ukv[i] = ((u32)x[i]) ^ 0x80000000u;
 }
 
 }  // namespace
@@ -457,8 +527,12 @@ int emap_create(const emap_config* cfg, int device, emap_handle** out) {
     if ((e = cudaEventRecord(h->in_free[b], h->stream)) != cudaSuccess) return bail("event", e);
   }
   if ((e = cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+  if ((e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+  if ((e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
   for (int k = 0; k < 9; k++) if ((e = cudaEventCreate(&h->st.ev[k])) != cudaSuccess) return bail("event", e);
 #define ALLOC(p, bytes) if ((e = cudaMalloc(&(p), (bytes))) != cudaSuccess) return bail("cudaMalloc", e)
+#define TRY(call) if ((e = (call)) != cudaSuccess) return bail(#call, e)
   ALLOC(h->map, sizeof(float) * 7 * C);
   ALLOC(h->map_alt, sizeof(float) * 7 * C);
   ALLOC(h->normal, sizeof(float) * 3 * C);
@@ -467,46 +541,80 @@ int emap_create(const emap_config* cfg, int device, emap_handle** out) {
   ALLOC(h->i64_block, sizeof(i64) * 3 * C);
   ALLOC(h->sc.last, sizeof(u64) * C);
   ALLOC(h->sc.rec, sizeof(uint2) * C);
+  ALLOC(h->sc.thr, sizeof(float) * C);
   ALLOC(h->sc.ukv, sizeof(u32) * C);
+  ALLOC(h->dirty, C + 16);
   ALLOC(h->ukey_x, sizeof(int) * C);
   ALLOC(h->fs, sizeof(FrameScalars));
-  ALLOC(h->steps, sizeof(float) * (h->steps_host.size() + 32));
+  ALLOC(h->lut, sizeof(unsigned short) * 65536);
+  ALLOC(h->tmap, sizeof(u32) * RT * RT);
   ALLOC(h->d_export, sizeof(float) * C);
+  // march table as k_raycast reads it: [0] unused (lane 0 of the first warp iteration), [1 + k] = s_k, +inf padding up to
+  // a whole number of 31-step warp iterations + one warp of over-read
+  h->n_tab = (int)(((h->steps_host.size() + RC_STRIDE - 1) / RC_STRIDE) * RC_STRIDE + 64) & ~1;
+  ALLOC(h->steps, sizeof(float) * h->n_tab);
 #undef ALLOC
-  h->sc.cnt_all = h->u32_block; h->sc.cnt_inl = h->u32_block + C; h->sc.cnt_fused = h->u32_block + 2 * C;
-  h->sc.n_out = h->u32_block + 3 * C; h->sc.n_ray = h->u32_block + 4 * C;
+  h->sc.cnt_ai = (u64*)h->u32_block; h->sc.cnt_fo = (u64*)(h->u32_block + 2 * C); h->sc.n_ray = h->u32_block + 4 * C;
   h->sc.SH = h->i64_block; h->sc.SV = h->i64_block + C; h->sc.DV = h->i64_block + 2 * C;
-  cudaMemsetAsync(h->u32_block, 0, sizeof(u32) * 5 * C, h->stream);
-  cudaMemsetAsync(h->i64_block, 0, sizeof(i64) * 3 * C, h->stream);
-  cudaMemsetAsync(h->sc.last, 0, sizeof(u64) * C, h->stream);
-  cudaMemsetAsync(h->sc.rec, 0, sizeof(uint2) * C, h->stream);
-  cudaMemsetAsync(h->sc.ukv, 0xff, sizeof(u32) * C, h->stream);      // UKEY_NONE
-  cudaMemsetAsync(h->normal, 0, sizeof(float) * 3 * C, h->stream);
-  cudaMemsetAsync(h->trav_input, 0, sizeof(float) * C, h->stream);
-  cudaMemsetAsync(h->fs, 0, sizeof(FrameScalars), h->stream);
-  {   // pad the march table to a multiple of 32 with +inf (k_raycast reads whole warps of steps)
-    std::vector<float> padded(h->steps_host);
-    while (padded.size() % 32 || padded.empty()) padded.push_back(INFINITY);
-    cudaMemcpy(h->steps, padded.data(), sizeof(float) * padded.size(), cudaMemcpyHostToDevice);
-  }
-  k_init<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map);
-  h->launches++;
-  if (post_smem(h->dc) > 48 * 1024)
-    cudaFuncSetAttribute(k_post<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(h->dc));
+  h->sc.dirty = h->dirty;
+  TRY(cudaMemsetAsync(h->u32_block, 0, sizeof(u32) * 5 * C, h->stream));
+  TRY(cudaMemsetAsync(h->i64_block, 0, sizeof(i64) * 3 * C, h->stream));
+  TRY(cudaMemsetAsync(h->sc.last, 0, sizeof(u64) * C, h->stream));
+  TRY(cudaMemsetAsync(h->sc.rec, 0, sizeof(uint2) * C, h->stream));
+  TRY(cudaMemsetAsync(h->sc.thr, 0, sizeof(float) * C, h->stream));
+  TRY(cudaMemsetAsync(h->sc.ukv, 0xff, sizeof(u32) * C, h->stream));      // UKEY_NONE
+  TRY(cudaMemsetAsync(h->dirty, 0, C + 16, h->stream));
+  TRY(cudaMemsetAsync(h->tmap, 0, sizeof(u32) * RT * RT, h->stream));
+  TRY(cudaMemsetAsync(h->normal, 0, sizeof(float) * 3 * C, h->stream));
+  TRY(cudaMemsetAsync(h->trav_input, 0, sizeof(float) * C, h->stream));
+  TRY(cudaMemsetAsync(h->fs, 0, sizeof(FrameScalars), h->stream));
   {
-    const int sm_bytes = (int)(sizeof(float) * ((h->steps_host.size() + 31) & ~(size_t)31));
-    if (sm_bytes > 40 * 1024) {
-      cudaFuncSetAttribute(k_raycast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes);
-      cudaFuncSetAttribute(k_raycast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes);
+    std::vector<float> tab((size_t)h->n_tab, INFINITY);
+    tab[0] = 0.f;
+    for (size_t k = 0; k < h->steps_host.size(); k++) tab[1 + k] = h->steps_host[k];
+    // pageable source: the copy is staged before the call returns, and the stream is synchronised below
+    TRY(cudaMemcpyAsync(h->steps, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, h->stream));
+    TRY(cudaStreamSynchronize(h->stream));
+  }
+  k_build_lut<<<256, 256, 0, h->stream>>>(h->dc, h->lut);
+  k_init<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map);
+  h->launches += 2;
+  if (post_smem(h->dc) > 48 * 1024)
+    TRY(cudaFuncSetAttribute(k_post<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(h->dc)));
+  {
+    {   // one warp iteration of the march: 30 steps between its first and last new sample, in cells (+1: fp16 coordinates)
+      double span = 0;
+      const std::vector<float>& st = h->steps_host;
+      for (size_t k = 0; k + 1 < st.size(); k++) {
+        const size_t e = std::min(st.size() - 1, k + RC_STRIDE - 1);
+        span = std::max(span, ((double)st[e] - (double)st[k]) / cfg->resolution);
+      }
+      h->span_cells = (int)std::ceil(span) + 2;
     }
+    {   // shared-memory layout of k_raycast: coarse maps + march table in the gap between the two halves of the cell
+        // table when they fit there, else behind the second half
+      const size_t P2 = (size_t)h->dc.lut_p2;
+      const size_t need = sizeof(float) * (RT * RT + (RT / 2) * (RT / 2) + (size_t)h->n_tab) + 16;
+      size_t base = (P2 + 15) & ~(size_t)15, end = 65536 + P2;
+      if (base + need > 65536) { base = (end + 15) & ~(size_t)15; end = base + need; }
+      h->rc_lay.off_t8 = (int)base;
+      h->rc_lay.off_t16 = (int)(base + sizeof(float) * RT * RT);
+      h->rc_lay.off_steps = (int)(base + sizeof(float) * (RT * RT + (RT / 2) * (RT / 2)));
+      h->rc_lay.off_bar = (int)((base + need - 16 + 7) & ~(size_t)7);
+      h->rc_smem = end;
+    }
+    TRY(cudaFuncSetAttribute(k_raycast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rc_smem));
+    TRY(cudaFuncSetAttribute(k_raycast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rc_smem));
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->n_sm = prop.multiProcessorCount;
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_raycast<false>, RC_THREADS, sm_bytes) == cudaSuccess && nb > 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_raycast<false>, RC_THREADS, h->rc_smem) == cudaSuccess && nb > 0)
       h->rc_blocks_per_sm = nb;
+    else h->rc_blocks_per_sm = 1;
   }
-  if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail("init", e);
-  if ((e = cudaGetLastError()) != cudaSuccess) return bail("init", e);
+  TRY(cudaStreamSynchronize(h->stream));
+  TRY(cudaGetLastError());
+#undef TRY
   *out = h;
   return EMAP_OK;
 }
@@ -519,10 +627,13 @@ int emap_destroy(emap_handle* h) {
   if (h->attached) { h->u32_block = nullptr; h->i64_block = nullptr; h->sc.last = nullptr; h->sc.rec = nullptr; h->sc.ukv = nullptr; h->fs = nullptr; }
   void* ptrs[] = {h->map, h->map_alt, h->normal, h->trav_input, h->u32_block, h->i64_block, h->sc.last, h->sc.rec,
                   h->sc.ukv, h->ukey_x, h->fs, h->steps, h->d_export, h->d_in[0], h->d_in[1], h->xyzv, h->pidx, h->pl[0], h->pl[1],
-                  h->pl[2], h->pl[3], h->pl_cnt, h->rays, h->ray_ctl};
+                  h->pl[2], h->pl[3], h->pl_cnt, h->rays, h->ray_ctl, h->sc.thr, h->dirty, h->lut, h->tmap, h->ip_block};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int b = 0; b < 2; b++) if (h->in_free[b]) cudaEventDestroy(h->in_free[b]);
   if (h->copy_done) cudaEventDestroy(h->copy_done);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }
   for (int k = 0; k < 9; k++) if (h->st.ev[k]) cudaEventDestroy(h->st.ev[k]);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -551,7 +662,7 @@ int emap_input_sensors(emap_handle* h, int32_t n_sensors, const void* const* poi
   ENTER(h);
   if (!points || !n || !R || !t) return fail(h, EMAP_ERR_INVALID, "emap_input: null argument");
   if (h->attached) return fail(h, EMAP_ERR_STATE, "handle is attached to a sharded scratch: use the emap_shard_* calls");
-  int rc = frame_begin(h, n_sensors, points, n, row_stride, dtype, is_device_ptr, R, t, 0, pn, on);
+  int rc = frame_begin(h, n_sensors, points, n, row_stride, dtype, is_device_ptr, R, t, 0, pn, on, false);
   if (rc) return rc;
   if ((rc = frame_index(h))) return rc;
   if ((rc = frame_fuse(h))) return rc;
@@ -576,7 +687,7 @@ int emap_shard_begin(emap_handle* h, int32_t n_sensors, const void* const* point
                      float on) {
   ENTER(h);
   if (!points || !n || !R || !t) return fail(h, EMAP_ERR_INVALID, "emap_shard_begin: null argument");
-  int rc = frame_begin(h, n_sensors, points, n, row_stride, dtype, is_device_ptr, R, t, global_point_offset, pn, on);
+  int rc = frame_begin(h, n_sensors, points, n, row_stride, dtype, is_device_ptr, R, t, global_point_offset, pn, on, true);
   if (rc) return rc;
   if (!is_device_ptr && !h->zero_copy_pending) CK(cudaEventSynchronize(h->copy_done));   // staged copy done: host buffers reusable
   // multicast mode: every rank must have reset its frame scalars before anyone pushes -> the caller runs a
@@ -613,8 +724,7 @@ int emap_shard_attach(emap_handle* h, void* local_base, void* multicast_base, in
   h->sc.rec = (uint2*)b; b += al256(8 * C);
   h->sc.ukv = (u32*)b; b += al256(4 * C);
   h->fs = (FrameScalars*)b;
-  h->sc.cnt_all = h->u32_block; h->sc.cnt_inl = h->u32_block + C; h->sc.cnt_fused = h->u32_block + 2 * C;
-  h->sc.n_out = h->u32_block + 3 * C; h->sc.n_ray = h->u32_block + 4 * C;
+  h->sc.cnt_ai = (u64*)h->u32_block; h->sc.cnt_fo = (u64*)(h->u32_block + 2 * C); h->sc.n_ray = h->u32_block + 4 * C;
   h->sc.SH = h->i64_block; h->sc.SV = h->i64_block + C; h->sc.DV = h->i64_block + 2 * C;
   h->sc.mc_off = (i64)((char*)multicast_base - (char*)local_base);
   CK(cudaMemsetAsync(local_base, 0, (size_t)emap_shard_scratch_bytes(h), h->stream));
@@ -638,19 +748,19 @@ int emap_shard_exchange(emap_handle* h, int32_t phase, emap_exchange* out, int32
   const i64 C = h->dc.C;
   if (phase == 1) {          // after begin: counts (CK.py:334,336) and the drift statistics (CK.py:332-333)
     if (h->phase != 1) return fail(h, EMAP_ERR_STATE, "exchange 1 must follow emap_shard_begin");
-    out[0] = {h->sc.cnt_all, 2 * C, 3};
+    out[0] = {h->sc.cnt_ai, 2 * C, 3};          // two 32-bit counters per cell: an int32 SUM keeps them apart
     out[1] = {&h->fs->E, 2, 0};
     *n_out = 2;
   } else if (phase == 2) {   // after fusion: sums, counts, last-writer keys
     if (h->phase != 2) return fail(h, EMAP_ERR_STATE, "exchange 2 must follow phase 1");
     out[0] = {h->sc.SH, 2 * C, 0};
-    out[1] = {h->sc.cnt_fused, 2 * C, 3};
+    out[1] = {h->sc.cnt_fo, 2 * C, 3};
     out[2] = {h->sc.last, C, 1};
     *n_out = 3;
   } else if (phase == 3) {   // after the ray-cast: decrements, counts, upper-bound keys
     if (h->phase != 3) return fail(h, EMAP_ERR_STATE, "exchange 3 must follow phase 2");
     if (h->dc.visibility) {
-      k_ukey_extract<<<cdiv(C, 256), 256, 0, h->stream>>>((int)C, h->sc.rec, h->sc.ukv, h->ukey_x);
+      k_ukey_extract<<<cdiv(C, 256), 256, 0, h->stream>>>((int)C, h->sc.ukv, h->ukey_x);
       LAUNCH_CHECK();
       out[0] = {h->sc.DV, C, 0};
       out[1] = {h->sc.n_ray, C, 3};
@@ -681,7 +791,7 @@ int emap_shard_phase(emap_handle* h, int32_t phase) {
   if (phase == 3) {
     if (h->phase != 3 && h->phase != 4) return fail(h, EMAP_ERR_STATE, "phase 3 must follow phase 2");
     if (h->phase == 4) {
-      k_ukey_merge<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc.C, h->sc.rec, h->sc.ukv, h->ukey_x);
+      k_ukey_merge<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc.C, h->sc.ukv, h->ukey_x);
       LAUNCH_CHECK();
     }
     return frame_finish(h);
@@ -962,8 +1072,77 @@ int emap_smooth_filter(emap_handle* h, const float* in, float* out) {
   return EMAP_OK;
 }
 
-int emap_inpaint(emap_handle* h, const float*, const float*, float*, int32_t) {
-  return fail(h, EMAP_ERR_INVALID, "emap_inpaint: not implemented in this build");
+// plugins/inpainting.py:53-63: 8-bit normalisation, cv.inpaint(h, mask, 1, INPAINT_TELEA), de-normalisation -- OpenCV's
+// fast-marching fill replayed on the device in parallel (emap_inpaint.cuh), bit-identical to cv2's result.
+int emap_inpaint(emap_handle* h, const float* elevation, const float* is_valid, float* out, int32_t method) {
+  ENTER(h);
+  if (!elevation || !is_valid || !out) return fail(h, EMAP_ERR_INVALID, "emap_inpaint: null argument");
+  if (method != 0) return fail(h, EMAP_ERR_INVALID, "emap_inpaint: only method 0 (telea) is implemented; 'ns' (Navier-Stokes) is not");
+  const int W = h->dc.W, rows = W + 2, cols = W + 2;
+  const size_t N = (size_t)rows * cols, C = (size_t)W * W;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  // f, ck, vc0, vc1 (u8 N) | img (u8 C) | T, Tc0, Tc1 (f32 N) | ord (u32 N) | heapA, heapB, children (int N) | ctl
+  const size_t need = 4 * al(N) + al(C) + 3 * al(4 * N) + al(4 * N) + 3 * al(4 * N) + al(sizeof(InpaintCtl));
+  if (h->ip_bytes < need) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->ip_block) cudaFree(h->ip_block);
+    h->ip_block = nullptr; h->ip_bytes = 0;
+    CK(cudaMalloc(&h->ip_block, need));
+    h->ip_bytes = need;
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_ip_march, 256, 0));
+    h->ip_grid = h->n_sm * std::max(1, std::min(nb, 2));
+  }
+  char* b = (char*)h->ip_block;
+  InpaintView v;
+  v.rows = rows; v.cols = cols;
+  v.f = (uint8_t*)b; b += al(N);
+  v.ck = (uint8_t*)b; b += al(N);
+  v.vc[0] = (uint8_t*)b; b += al(N);
+  v.vc[1] = (uint8_t*)b; b += al(N);
+  v.img = (uint8_t*)b; b += al(C);
+  v.T = (float*)b; b += al(4 * N);
+  v.Tc[0] = (float*)b; b += al(4 * N);
+  v.Tc[1] = (float*)b; b += al(4 * N);
+  v.ord = (uint32_t*)b; b += al(4 * N);
+  int* heapA = (int*)b; b += al(4 * N);
+  int* heapB = (int*)b; b += al(4 * N);
+  int* children = (int*)b; b += al(4 * N);
+  InpaintCtl* ctl = (InpaintCtl*)b;
+  InpaintCtl init;
+  memset(&init, 0, sizeof(init));
+  init.mm[0] = 0xffffffffu; init.mm[1] = 0u;
+  CK(cudaMemcpyAsync(ctl, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));     // pageable: staged before return
+  const int nbC = cdiv((i64)C, 256), nbN = cdiv((i64)N, 256);
+  k_ip_minmax<<<nbC, 256, 0, h->stream>>>((int)C, elevation, is_valid, ctl); LAUNCH_CHECK();
+  k_ip_init<<<nbN, 256, 0, h->stream>>>(W, elevation, is_valid, v, (const InpaintCtl*)ctl); LAUNCH_CHECK();
+  k_ip_band<<<nbN, 256, 0, h->stream>>>(v, heapA, ctl); LAUNCH_CHECK();
+  k_ip_band_flag<<<nbN, 256, 0, h->stream>>>(v, (const int*)heapA, ctl); LAUNCH_CHECK();
+  {
+    int cap = 4096;
+    void* args[] = {(void*)&v, (void*)&heapA, (void*)&heapB, (void*)&children, (void*)&ctl, (void*)&cap};
+    CK(cudaLaunchCooperativeKernel((const void*)k_ip_march, dim3(h->ip_grid), dim3(256), args, 0, h->stream));
+    h->launches++;
+  }
+  k_ip_finish<<<nbC, 256, 0, h->stream>>>((int)C, (const uint8_t*)v.img, elevation, out, (const InpaintCtl*)ctl); LAUNCH_CHECK();
+  return EMAP_OK;
+}
+
+// rounds / Jacobi statistics of the last emap_inpaint call (diagnostics)
+int emap_inpaint_stats(emap_handle* h, int32_t* rounds, int32_t* max_jacobi, int32_t* not_converged) {
+  ENTER(h);
+  if (!h->ip_block) return fail(h, EMAP_ERR_STATE, "emap_inpaint has not run");
+  const int W = h->dc.W;
+  const size_t N = (size_t)(W + 2) * (W + 2), C = (size_t)W * W;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t off = 4 * al(N) + al(C) + 3 * al(4 * N) + al(4 * N) + 3 * al(4 * N);
+  InpaintCtl c;
+  CK(cudaMemcpyAsync(&c, (char*)h->ip_block + off, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (rounds) *rounds = c.rounds;
+  if (max_jacobi) *max_jacobi = c.max_jacobi;
+  if (not_converged) *not_converged = c.not_converged;
+  return EMAP_OK;
 }
 
 // ---- plumbing --------------------------------------------------------------------------------

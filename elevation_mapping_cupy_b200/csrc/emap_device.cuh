@@ -50,6 +50,8 @@ struct DevCfg {
   float init_var, max_drift_f, drift_alpha_f, max_len16;
   float res_f;                 // CK.py:479-481 resolution() returns float
   float overlap_z_f, time_var_f, time_int_f;
+  u32 lut_lim2;                // half2 {LIM, LIM}: the march clamps fp16 coordinates to [-LIM, LIM] before the cell look-up
+  int lut_p2;                  // bytes of one half (positive / negative fp16 patterns) of the shared-memory cell table
   float w1[36], w2[36], w3[36], wout[12];
 };
 
@@ -59,7 +61,10 @@ struct Pose {                  // one sensor: R and t rounded to fp16 where the 
 
 struct __align__(16) Ray {     // one valid point's ray: set up once (CK.py:83-101,199-201,250)
   float x, y, z, len;          // end point (fp32) and fp16 march length
-  float rx, ry, rz, len_far;   // fp16 unit direction; samples with s < len_far are provably > sqrt(0.1) m from the end point
+  float rx, ry, rz;            // fp16 unit direction
+  u32 counts;                  // low 16 bits: n_act = number of march steps s_k < len (CK.py:203);
+                               // high 16 bits: k_far = number of steps s_k < len_far -- samples with k < k_far are
+                               // provably > sqrt(0.1) m from the end point (the `d < 0.1` test of CK.py:225 cannot fire)
 };
 
 struct FrameScalars {          // device-resident scalars of the running frame
@@ -125,6 +130,13 @@ __device__ __forceinline__ void axis_cell2(float inv_res, float half_w, float q_
     ix = min(max(__double2int_rz((double)x16 / c.resolution + c.half_w), 0), c.W - 1);
     iy = min(max(__double2int_rz((double)y16 / c.resolution + c.half_w), 0), c.W - 1);
   }
+}
+
+// CK.py:22-33 for EVERY fp16 bit pattern: lut[bits] = clamp(int(double(x16)/resolution + 0.5*W), 0, W-1).
+// An fp16 coordinate has only 65536 values, so the exact double expression is tabulated once per handle
+// (k_build_lut) and the ray march looks cells up instead of recomputing them (k_raycast).
+__device__ __forceinline__ int axis_cell_exact(const DevCfg& c, float c16) {
+  return min(max(__double2int_rz((double)c16 / c.resolution + c.half_w), 0), c.W - 1);
 }
 
 // CK.py:34-44

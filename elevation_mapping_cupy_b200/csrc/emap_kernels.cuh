@@ -19,21 +19,30 @@
 // ------------------------------------------------------------------------------------------
 // per-cell scratch of a frame; all zero between frames (k_finalize re-zeroes what it consumed)
 struct CellScratch {
-  u32* cnt_all;    // newmap[4]  CK.py:336
-  u32* cnt_inl;    // newmap[3]  CK.py:334
-  u32* cnt_fused;  // newmap[2]  CK.py:185
-  u32* n_out;      // number of atomicAdd(map[1], outlier_variance) by outlier points, CK.py:174
+  u64* cnt_ai;     // low word: newmap[4] all points of the cell (CK.py:336), high word: newmap[3] drift inliers (CK.py:334).
+                   // One 64-bit accumulation per point carries both (one multimem.red per run in sharded frames).
+  u64* cnt_fo;     // low word: newmap[2] fused points (CK.py:185), high word: atomicAdd(map[1], outlier_variance) count
+                   // of outlier points (CK.py:174)
   u32* n_ray;      // ... by penetrating rays, CK.py:251
   i64* SH;         // sum new_h   CK.py:183
   i64* SV;         // sum new_v   CK.py:184
   i64* DV;         // sum of validity decrements CK.py:250
   u64* last;       // (global point index << 32 | bits(new_h)) max  -> upper_bound of a hit cell, CK.py:191
-  uint2* rec;      // ray record, 8 B: {valid cell ? bits(h') : upper-bound key, flags}
-  u32* ukv;        // upper-bound key carved into VALID cells by penetrating rays (UKEY_NONE between frames)
+  float* thr;      // first-level ray record, 4 B: a sample at height nz can only act on the cell if !(nz > thr)
+  uint2* rec;      // second-level ray record, 8 B: {valid cell ? bits(h') : upper-bound key, flags}; read-only for rays
+  u32* ukv;        // min over rays of the upper-bound key carved into the cell (UKEY_NONE between frames), CK.py:230-233,253-256
+  unsigned char* dirty;   // 1 = some kernel of this frame touched the cell's scratch (k_finalize takes its full path there
+                   // and clears it); nullptr in sharded frames, where the marker is derived from cnt_all / ukv
   i64 mc_off;      // sharded frames: byte offset from a local scratch address to its NVLink MULTICAST alias
                    // (0 = single GPU).  Non-zero: every accumulation is one multimem.red that the NVSwitch
                    // applies to the replicas of ALL ranks (this one included) -- scatter and collective fused.
 };
+
+// Geometry of the cells a ray of this frame can reach, and of the coarse maps over them (ray_box in emap_api.cu):
+// rows [r0, r1) x columns [c0, c1) (c0, c1 multiples of 4 when W is); fine tiles of 2^ts x 2^ts cells, at most
+// RT x RT of them, origin (r0, c0).
+#define RT 64                     // fine tiles per axis of the coarse ray maps
+struct RayGrid { int r0, r1, c0, c1, ts; };
 
 // accumulate into the per-cell scratch: local L2 atomic, or one in-switch multicast reduction
 __device__ __forceinline__ void red_add(u32* p, u32 v, i64 mc) {
@@ -86,21 +95,50 @@ __device__ __forceinline__ i64 run_sum(i64 v, int lane, u32 run_mask) {
   return v;
 }
 
+// number of entries of the increasing table t[0..n) that are < x (binary search; NaN x -> 0)
+__device__ __forceinline__ int count_below(const float* __restrict__ t, int n, float x) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(t + mid) < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// One point's xyz.  fp32 rows padded to 4 floats (16-byte aligned): one 128-bit read-only load per point; other
+// layouts: three scalar loads (a warp's rows are contiguous, so they coalesce into the same sectors).
+template <typename T>
+__device__ __forceinline__ void load_point(const T* __restrict__ pts, i64 i, i64 stride, float& x, float& y, float& z) {
+  const T* p = pts + i * stride;
+  x = (float)p[0]; y = (float)p[1]; z = (float)p[2];
+}
+template <>
+__device__ __forceinline__ void load_point<float>(const float* __restrict__ pts, i64 i, i64 stride, float& x, float& y, float& z) {
+  const float* p = pts + i * stride;
+  if (stride == 4 && (reinterpret_cast<uintptr_t>(pts) & 15) == 0) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    x = v.x; y = v.y; z = v.z;
+  } else {
+    x = p[0]; y = p[1]; z = p[2];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64 n, const i64 stride,
               float4* __restrict__ xyzv, int* __restrict__ pidx, const float* __restrict__ map,
-              const CellScratch s, FrameScalars* fs, Ray* __restrict__ rays, int* __restrict__ ray_ctl) {
+              const CellScratch s, FrameScalars* fs, Ray* __restrict__ rays, int* __restrict__ ray_ctl,
+              const float* __restrict__ steps) {
   pdl_trigger(); pdl_wait();
   const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   i64 e = 0; int ec = 0, nv = 0;
-  Ray ray; ray.len = -1.f;
+  Ray ray; ray.len = -1.f; ray.counts = 0;
   int cell_key = -1 - (int)(threadIdx.x & 31);                    // cell receiving this point's count (unique negative: none)
   bool is_inl = false;
   if (i < n) {
-    const T* p = pts + i * stride;
-    float px = (float)p[0], py = (float)p[1], pz = (float)p[2];   // EM.py:456 cast to fp32
+    float px, py, pz;                                             // EM.py:456 cast to fp32
+    load_point(pts, i, stride, px, py, pz);
     int rec;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (px != px || py != py || pz != pz) {                       // EM.py:458 drop NaN rows
@@ -126,7 +164,9 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
         // bring it under 0.1) is therefore guaranteed for s < norm - (0.325 + 1e-3*(2m + 2 norm)).
         const float m = fmaxf(fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fabsf(g.z)),
                               fmaxf(fmaxf(fabsf(q.t[0]), fabsf(q.t[1])), fabsf(q.t[2])));
-        ray.len_far = norm - (0.325f + 1e-3f * (2.f * m + 2.f * norm));
+        const float len_far = norm - (0.325f + 1e-3f * (2.f * m + 2.f * norm));
+        // number of march steps below len / len_far: s_k is strictly increasing (steps[k] = s_k, +inf padded)
+        ray.counts = (u32)count_below(steps, c.n_steps, ray.len) | ((u32)count_below(steps, c.n_steps, len_far) << 16);
       }
       if (g.valid && g.inside) {                                  // CK.py:318-323
         const float mh = __ldg(map + idx), mv = __ldg(map + c.C + idx);
@@ -135,10 +175,10 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
             && (double)mv < c.inlier_var_half && (double)mt > c.trav_inlier) {   // CK.py:328-330
           e = fix32(g.z - mh); ec = 1;
           is_inl = true;
-          if (!s.mc_off) atomicAdd(s.cnt_inl + idx, 1u);
         }
         cell_key = idx;
-        if (!s.mc_off) atomicAdd(s.cnt_all + idx, 1u);
+        if (!s.mc_off) atomicAdd(s.cnt_ai + idx, is_inl ? 0x100000001ull : 1ull);
+        if (s.dirty) s.dirty[idx] = 1;
       }
     }
     xyzv[i] = o; pidx[i] = rec;
@@ -148,14 +188,13 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
     const RunInfo ri = run_of(cell_key, lane);
     const u32 inl = __ballot_sync(0xffffffffu, is_inl) & ri.run_mask;
     if (ri.tail && cell_key >= 0) {
-      red_add(s.cnt_all + cell_key, (u32)__popc(ri.run_mask), s.mc_off);
-      if (inl) red_add(s.cnt_inl + cell_key, (u32)__popc(inl), s.mc_off);
+      red_add(s.cnt_ai + cell_key, (u64)__popc(ri.run_mask) | ((u64)__popc(inl) << 32), s.mc_off);
     }
   }
   // compact the rays that have at least one march step (s_0 < len) into the sensor's ray list: one
   // atomic per CTA; the list order is irrelevant (every ray effect is a commutative integer atomic)
   __shared__ int s_rc[9];
-  const bool has_ray = ray.len > c.first_step;
+  const bool has_ray = (ray.counts & 0xffffu) != 0;               // at least one march step: s_0 < len
   const u32 ray_bal = __ballot_sync(0xffffffffu, has_ray);
   if ((threadIdx.x & 31) == 0) s_rc[threadIdx.x >> 5] = __popc(ray_bal);
   // block reduction -> one integer atomic per block (order independent)
@@ -183,7 +222,7 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
     for (int k = 0; k < w; k++) base += s_rc[k];
     float4* dst = reinterpret_cast<float4*>(rays + base + __popc(ray_bal & ((1u << l) - 1u)));
     dst[0] = make_float4(ray.x, ray.y, ray.z, ray.len);
-    dst[1] = make_float4(ray.rx, ray.ry, ray.rz, ray.len_far);
+    dst[1] = make_float4(ray.rx, ray.ry, ray.rz, __uint_as_float(ray.counts));
   }
 }
 
@@ -195,11 +234,12 @@ __global__ void k_set_overlap(FrameScalars* fs, float overlap_tz) {
 // EM.py:346-357
 // Also the frame's housekeeping, so that no separate reset launch is needed: the drift accumulators are
 // consumed here and zeroed for the NEXT frame, the ray-march counters of the previous frame are cleared, the
-// overlap-clear reference is set, and the other half of the double-buffered ray work counters is zeroed.
+// overlap-clear reference is set, and the coarse ray map is reset.  (The ray work counters are re-zeroed by
+// k_finalize, after the ray-cast: every frame is the same launch sequence -> capturable as one CUDA graph.)
 __global__ void k_drift(const DevCfg c, FrameScalars* fs, float position_noise, float orientation_noise,
-                        float overlap_tz, int set_overlap, int* ray_ctl_next, int n_ctl) {
+                        float overlap_tz, int set_overlap, u32* __restrict__ tmap) {
   pdl_trigger(); pdl_wait();
-  for (int k = threadIdx.x; k < n_ctl; k += blockDim.x) ray_ctl_next[k] = 0;
+  for (int k = threadIdx.x; k < RT * RT; k += blockDim.x) tmap[k] = 0u;       // below every key: fkey(-inf) = 0x007fffff
   if (threadIdx.x || blockIdx.x) return;
   const i64 ecnt = fs->ecnt;
   const float error_sum = (float)unfix32(fs->E);
@@ -219,6 +259,10 @@ __global__ void k_drift(const DevCfg c, FrameScalars* fs, float position_noise, 
 }
 
 // CK.py:168-197 fusion half; every load is of the pre-frame snapshot (+ drift shift)
+// PUSH: bit 0 = the counts (cnt_fo: needed by the ray-cast), bit 1 = the sums and last-writer keys (needed only by
+// k_finalize).  Single GPU: 3.  Sharded frames over NVLink multicast launch it twice: <1> on the critical path and <2>
+// on a side stream under the ray-cast, so that three of the four multicast reductions per run leave the critical path.
+template <int PUSH>
 __global__ void __launch_bounds__(256)
 k_fuse(const DevCfg c, const i64 n, const i64 global_off, const float4* __restrict__ xyzv,
        const int* __restrict__ pidx, const float* __restrict__ map, const CellScratch s,
@@ -239,7 +283,7 @@ k_fuse(const DevCfg c, const i64 n, const i64 global_off, const float4* __restri
       float mh = __ldg(map + idx);
       if (fs->applied) mh = __fadd_rn(mh, fs->shift);             // EM.py:357 applied lazily
       const float mv = __ldg(map + c.C + idx);
-      const float num_points = (float)s.cnt_all[idx];             // CK.py:172
+      const float num_points = (float)(u32)s.cnt_ai[idx];         // CK.py:172
       if ((double)fabsf(mh - z) > (double)mv * c.mahal) {
         is_out = true;                                            // CK.py:174
       } else if (c.edge_sharpen && (double)num_points > c.wall_thresh
@@ -255,11 +299,10 @@ k_fuse(const DevCfg c, const i64 n, const i64 global_off, const float4* __restri
     }
   }
   if (!s.mc_off) {                        // single GPU: plain L2 atomics
-    if (is_out) atomicAdd(s.n_out + idx, 1u);
-    if (is_fused) {
+    if ((PUSH & 1) && (is_out || is_fused)) atomicAdd(s.cnt_fo + idx, is_out ? 0x100000000ull : 1ull);
+    if ((PUSH & 2) && is_fused) {
       atomicAdd((u64*)(s.SH + idx), (u64)fh);
       atomicAdd((u64*)(s.SV + idx), (u64)fv);
-      atomicAdd(s.cnt_fused + idx, 1u);
       atomicMax(s.last + idx, key);
     }
     return;
@@ -271,11 +314,10 @@ k_fuse(const DevCfg c, const i64 n, const i64 global_off, const float4* __restri
   const i64 sh = run_sum(fh, lane, ri.run_mask), sv = run_sum(fv, lane, ri.run_mask);
   const u64 top_key = __shfl_sync(0xffffffffu, key, fus ? 31 - __clz(fus) : lane);   // highest fused lane = latest point
   if (ri.tail && idx >= 0) {
-    if (outs) red_add(s.n_out + idx, (u32)__popc(outs), s.mc_off);
-    if (fus) {
+    if ((PUSH & 1) && (outs | fus)) red_add(s.cnt_fo + idx, (u64)__popc(fus) | ((u64)__popc(outs) << 32), s.mc_off);
+    if ((PUSH & 2) && fus) {
       red_add((u64*)(s.SH + idx), (u64)sh, s.mc_off);
       red_add((u64*)(s.SV + idx), (u64)sv, s.mc_off);
-      red_add(s.cnt_fused + idx, (u32)__popc(fus), s.mc_off);
       red_max(s.last + idx, top_key, s.mc_off);
     }
   }
@@ -292,6 +334,10 @@ template <int V, typename T> __device__ __forceinline__ void stv(T* p, const T (
   else if (V == 4) { uint4 t; ((T*)&t)[0] = a[0]; ((T*)&t)[1] = a[1 % V]; ((T*)&t)[2] = a[2 % V]; ((T*)&t)[3] = a[3 % V]; *reinterpret_cast<uint4*>(p) = t; }
   else { for (int j = 0; j < V; j++) p[j] = a[j]; }
 }
+template <int V> __device__ __forceinline__ void ldv64(const u64* p, u64 (&a)[V]) {     // V u64: 16-byte accesses when V is even
+  if (V % 2 == 0) { for (int j = 0; j < V; j += 2) { const uint4 t = *reinterpret_cast<const uint4*>(p + j); a[j] = ((u64)t.y << 32) | t.x; a[(j + 1) % V] = ((u64)t.w << 32) | t.z; } }
+  else { for (int j = 0; j < V; j++) a[j] = p[j]; }
+}
 template <int V, typename T> __device__ __forceinline__ bool anyv(const T (&a)[V]) { bool r = false; for (int j = 0; j < V; j++) r |= (a[j] != (T)0); return r; }
 template <int V, typename T> __device__ __forceinline__ bool diffv(const T (&a)[V], const T (&b)[V]) { bool r = false; for (int j = 0; j < V; j++) r |= (a[j] != b[j]); return r; }
 
@@ -301,27 +347,42 @@ __device__ __forceinline__ float add_n_times(float v, float c, u32 n) {
   return v;
 }
 
-// post-fusion state of a cell as a ray sees it (SURVEY 8(c) step 3 -> 4), packed to 8 B:
-//   .x = bits(h' = h (+ drift shift))            for cells that are valid after the fusion stores
-//      = upper-bound key (UKEY_NONE if unbounded) for invalid cells -- rays atomicMin it in place
-//   .y = RF_* flags
-// The variance a ray needs (CK.py:239) is rebuilt on the rare second level from map[1] and n_out.
-// V consecutive cells per thread, every plane read as one vector up front (HBM-bound pass).
-// Also re-zeroes cnt_all / cnt_inl: no later kernel of the frame reads them.
+// Post-fusion state of a cell as a ray sees it (SURVEY 8(c) step 3 -> 4), in two levels:
+//   thr (4 B)  first level.  A ray sample at height nz can act on the cell only if !(nz > thr):
+//                invalid cell              thr = its upper bound (+inf if unbounded): a sample carves only below it, CK.py:230
+//                valid, time < 0.5, border thr = -inf: CK.py:237 / CK.py:211, never
+//                valid otherwise           thr = h' + 0.06 (and fl(thr - 0.05f) > h' checked), so nz > thr implies the
+//                                          far-below rejection `h' < nz - 0.05f` the second level would take (CK.py:239)
+//   rec (8 B)  second level, read only by the few samples that pass: .x = bits(h' = h (+ drift shift)) for valid
+//              cells / upper-bound key for invalid ones, .y = RF_* flags.
+// The variance a ray needs (CK.py:239) is rebuilt on the second level from map[1] and n_out.
+// Only the cells a ray of this frame can reach are recorded: box = sensor cell +- (max_ray_length / resolution + slack),
+// rows [box.x, box.y) x columns [box.z, box.w) (columns a multiple of V), computed on the host (ray_box in emap_api.cu).
+// Also reduces thr to the coarse map tmap: max over each 2^ts x 2^ts tile (order-preserving keys, atomicMax; zeroed
+// by k_drift) -- a ray above a tile's maximum cannot act on any of its cells (k_raycast).
 template <int V>
 __global__ void __launch_bounds__(256)
-k_record(const DevCfg c, const float* __restrict__ map, const CellScratch s, const FrameScalars* __restrict__ fs) {
+k_record(const DevCfg c, const float* __restrict__ map, const CellScratch s, const FrameScalars* __restrict__ fs, const RayGrid g,
+         u32* __restrict__ tmap) {
   pdl_trigger(); pdl_wait();
-  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * V;
-  if (i0 >= c.C) return;
+  const int ncg = (g.c1 - g.c0) / V;                              // column groups per row
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncg * (g.r1 - g.r0)) return;
+  const int rr = g.r0 + t / ncg, cc0 = g.c0 + (t % ncg) * V;
+  const int i0 = rr * c.W + cc0;
   const size_t C = (size_t)c.C;
   float h4[V], va4[V], ti4[V], up4[V], iu4[V];
-  u32 cf4[V], ci4[V], ca4[V];
+  u32 cf4[V], ci4[V];
   ldv<V>(map + i0, h4); ldv<V>(map + 2 * C + i0, va4); ldv<V>(map + 4 * C + i0, ti4);
   ldv<V>(map + 5 * C + i0, up4); ldv<V>(map + 6 * C + i0, iu4);
-  ldv<V>(s.cnt_fused + i0, cf4); ldv<V>(s.cnt_inl + i0, ci4); ldv<V>(s.cnt_all + i0, ca4);
+  {
+    u64 fo[V], ai[V];
+    ldv64<V>(s.cnt_fo + i0, fo); ldv64<V>(s.cnt_ai + i0, ai);
+    for (int j = 0; j < V; j++) { cf4[j] = (u32)fo[j]; ci4[j] = (u32)(ai[j] >> 32); }
+  }
   const int applied = fs->applied; const float shift = fs->shift;
-  u32 oa[V], ofl[V];
+  const float inf = __int_as_float(0x7f800000);
+  u32 oa[V], ofl[V]; float ot[V];
 #pragma unroll
   for (int j = 0; j < V; j++) {
     float valid = va4[j], time = ti4[j];
@@ -329,20 +390,32 @@ k_record(const DevCfg c, const float* __restrict__ map, const CellScratch s, con
     if (hit) { valid = 1.f; time = 0.f; }                                    // CK.py:187-192
     u32 fl = (time < 0.5f ? RF_T05 : 0u) | (time < 1.0f ? RF_T10 : 0u)
            | ((double)(float)ci4[j] > c.wall_thresh ? RF_WALL : 0u);
-    u32 a;
+    u32 a; float th;
     if (valid < 0.5f) {
-      a = (hit || iu4[j] < 0.5f) ? UKEY_NONE : fkey(up4[j]);
+      const bool unbounded = hit || iu4[j] < 0.5f;
+      a = unbounded ? UKEY_NONE : fkey(up4[j]);
+      th = unbounded ? inf : up4[j];                                         // NaN bound: `nz > NaN` never skips
     } else {
       fl |= RF_VALID;
       float h = h4[j];
       if (applied) h = __fadd_rn(h, shift);
       a = __float_as_uint(h);
+      th = __fadd_rn(h, 0.06f);
+      if (!(__fsub_rn(th, 0.05f) > h)) th = inf;                             // huge / NaN heights: never skip
+      if (fl & RF_T05) th = -inf;
     }
-    {   // border ring: make every ray skip the cell (see RF_* in emap_device.cuh); .x stays the cell's own key
-      const int i = i0 + j, rr = i / c.W, cc = i - rr * c.W;
-      if (rr == 0 || rr == c.W - 1 || cc == 0 || cc == c.W - 1) fl = RF_VALID | RF_T05 | RF_T10;
+    {   // border ring: make every ray skip the cell (see RF_* in emap_device.cuh)
+      const int cc = cc0 + j;
+      if (rr == 0 || rr == c.W - 1 || cc == 0 || cc == c.W - 1) { fl = RF_VALID | RF_T05 | RF_T10; th = -inf; }
     }
-    oa[j] = a; ofl[j] = fl;
+    oa[j] = a; ofl[j] = fl; ot[j] = th;
+  }
+  stv<V>(s.thr + i0, ot);
+  {   // V cells of one row lie in one tile (V <= 4 <= 2^ts, cc0 - c0 a multiple of V)
+    float m = -inf;
+#pragma unroll
+    for (int j = 0; j < V; j++) m = fmaxf(m, (ot[j] != ot[j]) ? inf : ot[j]);     // NaN threshold: never cull
+    if (m > -inf) atomicMax(tmap + (((rr - g.r0) >> g.ts) * RT + ((cc0 - g.c0) >> g.ts)), fkey(m));
   }
   if (V == 4) {
     uint4* dst = reinterpret_cast<uint4*>(s.rec + i0);
@@ -351,98 +424,215 @@ k_record(const DevCfg c, const float* __restrict__ map, const CellScratch s, con
   } else {
     for (int j = 0; j < V; j++) s.rec[i0 + j] = make_uint2(oa[j], ofl[j]);
   }
-  const u32 zero[V] = {};
-  if (anyv<V>(ca4)) stv<V>(s.cnt_all + i0, zero);
-  if (anyv<V>(ci4)) stv<V>(s.cnt_inl + i0, zero);
+}
+
+// fill the per-handle cell table (all 65536 fp16 bit patterns, CK.py:22-33 in its exact double form)
+__global__ void __launch_bounds__(256) k_build_lut(const DevCfg c, unsigned short* __restrict__ lut) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= 65536) return;
+  lut[b] = (unsigned short)axis_cell_exact(c, __half2float(__ushort_as_half((unsigned short)b)));
 }
 
 // CK.py:198-259 ray-cast half as a persistent kernel.  The rays of the frame were set up and compacted
 // by k_index_error; every WARP pulls the next ray from a global work counter (dynamic balancing: ray
-// lengths differ by 100x) and marches it with its 32 lanes on 32 consecutive steps of the fp16 march
+// lengths differ by 100x) and marches it with its 32 lanes on consecutive steps of the fp16 march
 // variable s_k (shared table: s_0 = half(step), s_{k+1} = half(float(double(s_k) + step)), CK.py:203).
-// "Same cell as the previous step" (CK.py:209-210) is a shuffle with the neighbouring lane.  The
-// effects of a visit are commutative integer atomics, so neither lane nor ray order matters.
-#define RC_THREADS 128
+//   * cell of a sample: the fp16 coordinates half(t + ray*s_k) (CK.py:205-207,26-33) index a shared-memory
+//     table of the exact cell of every fp16 value (TMA bulk copy of the handle's table, issued before the
+//     dependency wait); coordinates are first clamped to [-LIM, LIM] (packed half2 min/max), beyond which
+//     every value maps to cell 0 / W-1 anyway, so only the patterns [0, P) and [0x8000, 0x8000 + P) are staged.
+//   * "same cell as the previous step" (CK.py:209-210) is a shuffle with the neighbouring lane; warp iterations
+//     overlap by one step (lane 0 re-derives the last cell of the previous iteration and never visits).
+//   * first level: one 4-byte load decides whether the sample can act at all (see k_record); the few that can
+//     take the exact second level.  The effects of a visit are commutative integer atomics, so neither lane
+//     nor ray order matters.
+#define RC_THREADS 768
+#define RC_STRIDE 31              // new march steps per warp iteration
+#define RC_BATCH 4                // rays a warp draws from the work counter at a time
+struct RcLayout { int off_t8, off_t16, off_steps, off_bar; };     // byte offsets of the shared-memory regions (host: rc_layout)
+
+// cell of the sample t + ray*s (CK.py:205-207 -> 26-33) through the staged table; all lanes must pass in-range addresses
+__device__ __forceinline__ void rc_cell(const u32 s_lut, const u32 lim2, const u32 nlim2, const float nx, const float ny,
+                                        u32& ix, u32& iy) {
+  u32 xy;                                                         // {half(nx), half(ny)} clamped to [-LIM, LIM] (NaN -> -LIM -> cell 0)
+  asm("{ .reg .b32 t; cvt.rn.f16x2.f32 t, %2, %1; max.f16x2 t, t, %3; min.f16x2 %0, t, %4; }"
+      : "=r"(xy) : "f"(nx), "f"(ny), "r"(nlim2), "r"(lim2));
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ix) : "r"(s_lut + ((xy & 0xffffu) << 1)));
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(iy) : "r"(s_lut + ((xy >> 16) << 1)));
+}
+
 template <bool COUNT>
-__global__ void __launch_bounds__(RC_THREADS)
+__global__ void __launch_bounds__(RC_THREADS, 2)
 k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __restrict__ ray_ctl,
           const float* __restrict__ map, const float* __restrict__ normal,
-          const CellScratch s, const float* __restrict__ steps, FrameScalars* fs) {
-  extern __shared__ float s_steps[];             // n_steps padded to a multiple of 32 with +inf
+          const CellScratch s, const float* __restrict__ steps_tab, const int n_tab,
+          const unsigned short* __restrict__ lut, const RayGrid g, const u32* __restrict__ tmap, const RcLayout lay,
+          FrameScalars* fs) {
+  // shared: [0, P2) cells of the non-negative fp16 patterns | [65536, 65536 + P2) negative patterns; in the gap between
+  // them (or behind, if it is too small): coarse maps t8 (RT x RT) and t16 (RT/2 x RT/2), the march table
+  // (n_tab floats: [0] dummy, [1 + k] = s_k, +inf padded) and the mbarrier of the bulk copies
+  extern __shared__ __align__(128) unsigned char s_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int n_pad = (c.n_steps + 31) & ~31;
+  const int P2 = c.lut_p2;
+  float* s_steps = reinterpret_cast<float*>(s_raw + lay.off_steps);
+  float* s_t8 = reinterpret_cast<float*>(s_raw + lay.off_t8);
+  float* s_t16 = reinterpret_cast<float*>(s_raw + lay.off_t16);
+  const u32 s_lut = (u32)__cvta_generic_to_shared(s_raw);
+  const u32 sbar = s_lut + (u32)lay.off_bar;
   pdl_trigger();
-  for (int k = tid; k < n_pad; k += RC_THREADS) s_steps[k] = steps[k];      // static table: before the dependency wait
-  __syncthreads();
+  // static tables (written once at emap_create): staged before the dependency wait, under the previous kernel's tail
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbar), "r"(2 * P2) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s_lut), "l"(lut), "r"(P2), "r"(sbar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s_lut + 65536u), "l"(lut + 32768), "r"(P2), "r"(sbar) : "memory");
+  }
+  for (int k = tid; k < n_tab; k += RC_THREADS) s_steps[k] = steps_tab[k];
   pdl_wait();
+  // coarse maps of this frame (k_record): t8[a][b] = max thr over fine tile (a, b); t16[A][B] = max over the 3 x 3 block
+  // of double-size tiles whose first one is (A, B), i.e. fine tiles [2A, 2A+6) x [2B, 2B+6): a warp iteration (31 steps,
+  // < 22 cells per axis) whose first-corner tile is (A, B) stays inside that block.
+  for (int k = tid; k < RT * RT; k += RC_THREADS) s_t8[k] = funkey(tmap[k] ? tmap[k] : 0x007fffffu);
+  __syncthreads();
+  for (int k = tid; k < (RT / 2) * (RT / 2); k += RC_THREADS) {
+    const int A = k / (RT / 2), B = k - A * (RT / 2);
+    float m = __int_as_float(0xff800000);                         // k_record never stores a NaN key
+    for (int i = 0; i < 6; i++)
+      for (int j = 0; j < 6; j++)
+        if (2 * A + i < RT && 2 * B + j < RT) m = fmaxf(m, s_t8[(2 * A + i) * RT + 2 * B + j]);
+    s_t16[k] = m;
+  }
+  __syncthreads();
+  {
+    u32 ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(sbar), "r"(0) : "memory");
+  }
   const int n_rays = ray_ctl[0];
   int* next = ray_ctl + 1;
   const int W = c.W, C = c.C;
   const float tx = q.t[0], ty = q.t[1], tz = q.t[2];
-  const float inv_res = c.inv_res_f, half_w = c.half_w_f, q_hi = (float)c.W - 0.75f;
-  const u32 s_lane = (u32)__cvta_generic_to_shared(s_steps) + 4u * lane;     // shared-space address of s_steps[lane]
+  const u32 lim2 = c.lut_lim2, nlim2 = c.lut_lim2 ^ 0x80008000u;
+  const u32 s_steps_a = s_lut + (u32)lay.off_steps;               // shared-space address of s_tab[0]
+  const u32 s_t8_a = s_lut + (u32)lay.off_t8, s_t16_a = s_lut + (u32)lay.off_t16;
+  const int ts = g.ts;
   int n_steps_done = 0, n_visits = 0;
+  // Work queue: one global counter; a warp draws RC_BATCH consecutive rays per atomic (all warps hammering ONE address
+  // serialise at ~0.8 ns per atomic, which bounded the kernel at one ray per atomic) and prefetches its next batch
+  // while it marches the current one.
   int pend = 0;
-  if (lane == 0) pend = atomicAdd(next, 1);
-  int r = __shfl_sync(0xffffffffu, pend, 0);
-  while (r < n_rays) {
-    if (lane == 0) pend = atomicAdd(next, 1);                     // next ray: latency hidden by this march
-    const float4 ra = __ldg(reinterpret_cast<const float4*>(rays + r));
+  if (lane == 0) pend = atomicAdd(next, RC_BATCH);
+  int rbase = __shfl_sync(0xffffffffu, pend, 0);
+  while (rbase < n_rays) {
+    if (lane == 0) pend = atomicAdd(next, RC_BATCH);              // next batch: latency hidden by this one's march
+   for (int r = rbase; r < min(rbase + RC_BATCH, n_rays); r++) {
     const float4 rb = __ldg(reinterpret_cast<const float4*>(rays + r) + 1);
-    const float x = ra.x, y = ra.y, z = ra.z, len = ra.w, rx = rb.x, ry = rb.y, rz = rb.z;
-    const i64 dec_fix = fix32((float)(-c.cleanup_step / ((double)len / c.max_ray_length)));   // CK.py:250
-    const float len_far = rb.w;
-    int carry = -1;
-    for (int kb = 0; kb < n_pad; kb += 32) {
-      float sk;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sk) : "r"(s_lane + 4u * kb));
-      const bool act = sk < len;
-      if (!__any_sync(0xffffffffu, act)) break;
-      const float nx = __fmaf_rn(rx, sk, tx);                     // t + ray*s: product exact (CK.py:205-207)
-      const float ny = __fmaf_rn(ry, sk, ty);
-      int ix, iy;
-      axis_cell2(inv_res, half_w, q_hi, c, h16(nx), h16(ny), ix, iy);
-      const int nidx = act ? ix * W + iy : -2;
-      int prev = __shfl_up_sync(0xffffffffu, nidx, 1);
-      if (lane == 0) prev = carry;
-      carry = __shfl_sync(0xffffffffu, nidx, 31);
-      if (COUNT) n_steps_done += act;
-      if (nidx == prev || !act) continue;                         // CK.py:209 (CK.py:211: border cells are skipped via their record flags)
-      const float nz = __fmaf_rn(rz, sk, tz);
-      // CK.py:225-226 `d < 0.1` (d = fp16 of the squared distance to the end point) cannot fire for
-      // s < len_far (bound derived where the ray is set up, k_index_error).
-      if (!(sk < len_far)) {
-        const float ddx = x - nx, ddy = y - ny, ddz = z - nz;
-        float d = __fmul_rn(ddy, ddy); d = __fmaf_rn(ddx, ddx, d); d = __fmaf_rn(ddz, ddz, d);
-        d = h16(d);
-        if (d < 0.1f) continue;    // `d < 0.1` in double: no fp16 value lies in [0.1, 0.1f)
-      }
-      if (COUNT) n_visits++;
-      const uint2 rc = s.rec[nidx];
-      if (!(rc.y & RF_VALID)) {                                   // CK.py:229-235 carve the upper bound
-        const u32 key = fkey(nz);
-        if (key < rc.x) {
-          if (!s.mc_off) atomicMin(&s.rec[nidx].x, key);          // single GPU: the record itself carries the min
-          else if (key < __ldcg(s.ukv + nidx)) red_min(s.ukv + nidx, key, s.mc_off);   // sharded: min over all ranks
+    const float rx = rb.x, ry = rb.y, rz = rb.z;
+    const int n_act = (int)(__float_as_uint(rb.w) & 0xffffu), k_far = (int)(__float_as_uint(rb.w) >> 16);
+    const int n_it = (n_act + RC_STRIDE - 1) / RC_STRIDE;
+    for (int it0 = 0; it0 < n_it; it0 += 32) {
+      // ---- which of the next 32 warp iterations can act at all: lane L decides iteration it0 + L from the cells of its
+      // first and last step (coordinates are monotone along the ray, so they bound the iteration's cells) and the lower of
+      // the two sample heights, against the 3 x 3-block maximum of the coarse map
+      u32 todo;
+      {
+        const int it = it0 + lane;
+        bool live = it < n_it;
+        const int ka = min(it * RC_STRIDE, n_act - 1), kb = min(it * RC_STRIDE + RC_STRIDE - 1, n_act - 1);
+        float sa, sb;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sa) : "r"(s_steps_a + 4u * (u32)(max(ka, 0) + 1)));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sb) : "r"(s_steps_a + 4u * (u32)(max(kb, 0) + 1)));
+        u32 ixa, iya, ixb, iyb;
+        rc_cell(s_lut, lim2, nlim2, __fmaf_rn(rx, sa, tx), __fmaf_rn(ry, sa, ty), ixa, iya);
+        rc_cell(s_lut, lim2, nlim2, __fmaf_rn(rx, sb, tx), __fmaf_rn(ry, sb, ty), ixb, iyb);
+        const float zmin = fminf(__fmaf_rn(rz, sa, tz), __fmaf_rn(rz, sb, tz));
+        const int A = ((int)min(ixa, ixb) - g.r0) >> (ts + 1), B = ((int)min(iya, iyb) - g.c0) >> (ts + 1);
+        if (live && !COUNT && (unsigned)A < RT / 2 && (unsigned)B < RT / 2) {
+          float m;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m) : "r"(s_t16_a + 4u * (u32)(A * (RT / 2) + B)));
+          if (zmin > m) live = false;                             // NaN on either side: stays live
         }
-        continue;
+        todo = __ballot_sync(0xffffffffu, live);
       }
-      if (rc.y & RF_T05) continue;                                // CK.py:237
-      const float nh = __uint_as_float(rc.x);
-      // CK.py:239 needs nh > nz + 0.01 - min(v,1)*0.05 >= nz - 0.04: reject far-below cells in fp32
-      if (nh < nz - 0.05f) continue;
-      const float nv = add_n_times(__ldg(map + C + nidx), c.c_out, s.n_out[nidx]);
-      const double rhs = fma(-fmin((double)nv, 1.0), 0.05, (double)nz + 0.01);   // CK.py:239 (nvcc contraction)
-      if (!((double)nh > rhs)) continue;
-      const float n0 = h16(__ldg(normal + nidx)), n1 = h16(__ldg(normal + C + nidx)), n2 = h16(__ldg(normal + 2 * C + nidx));
-      const float product = __fadd_rn(__fadd_rn(__fmul_rn(rx, n0), __fmul_rn(ry, n1)), __fmul_rn(rz, n2));   // CK.py:103-108
-      if ((double)fabsf(product) < c.cos_thresh) continue;        // CK.py:245
-      if ((rc.y & RF_WALL) && (rc.y & RF_T10)) continue;          // CK.py:246-247
-      red_add((u64*)(s.DV + nidx), (u64)dec_fix, s.mc_off);       // CK.py:250
-      red_add(s.n_ray + nidx, 1u, s.mc_off);                      // CK.py:251
-      red_min(s.ukv + nidx, fkey(nz), s.mc_off);                  // CK.py:253-256
+      while (todo) {
+        const int it = it0 + __ffs(todo) - 1;
+        todo &= todo - 1;
+        // lane l handles step k = it*31 + l - 1 (k = -1: none); lane 0 only supplies the previous cell
+        const int k = it * RC_STRIDE + lane - 1;
+        float sk;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sk) : "r"(s_steps_a + 4u * (u32)(k + 1)));
+        const bool act = (unsigned)k < (unsigned)n_act;
+        const float nx = __fmaf_rn(rx, sk, tx);                   // t + ray*s: product exact (CK.py:205-207)
+        const float ny = __fmaf_rn(ry, sk, ty);
+        u32 ix, iy;
+        rc_cell(s_lut, lim2, nlim2, nx, ny, ix, iy);
+        const int nidx = act ? (int)(ix * (u32)W + iy) : -2;
+        const int prev = __shfl_up_sync(0xffffffffu, nidx, 1);    // lane 0 gets its own value back: never visits
+        if (COUNT) n_steps_done += act && lane != 0;
+        if (nidx == prev || !act) continue;                       // CK.py:209 (CK.py:211: border cells are skipped via thr = -inf)
+        const float nz = __fmaf_rn(rz, sk, tz);
+        if (!COUNT) {   // coarse level: the fine tile's maximum
+          const int a = ((int)ix - g.r0) >> ts, b = ((int)iy - g.c0) >> ts;
+          if ((unsigned)a < RT && (unsigned)b < RT) {
+            float m;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m) : "r"(s_t8_a + 4u * (u32)(a * RT + b)));
+            if (nz > m) continue;
+          }
+        }
+        if (COUNT) {   // statistics mode: count the cells examined past the skips of CK.py:209-226, as the oracle does
+          bool near = false;
+          if (k >= k_far) {
+            const float4 ra = __ldg(reinterpret_cast<const float4*>(rays + r));
+            const float ddx = ra.x - nx, ddy = ra.y - ny, ddz = ra.z - nz;
+            float d = __fmul_rn(ddy, ddy); d = __fmaf_rn(ddx, ddx, d); d = __fmaf_rn(ddz, ddz, d);
+            near = h16(d) < 0.1f;
+          }
+          if (!near) n_visits++;
+        }
+        if (nz > __ldg(s.thr + nidx)) continue;                   // first level: the sample cannot act on this cell
+        // ---- second level (rare): the exact tests of CK.py:225-256
+        const float4 ra = __ldg(reinterpret_cast<const float4*>(rays + r));      // end point, march length
+        if (k >= k_far) {
+          // CK.py:225-226 `d < 0.1` (d = fp16 of the squared distance to the end point); cannot fire for k < k_far
+          // (bound derived where the ray is set up, k_index_error)
+          const float ddx = ra.x - nx, ddy = ra.y - ny, ddz = ra.z - nz;
+          float d = __fmul_rn(ddy, ddy); d = __fmaf_rn(ddx, ddx, d); d = __fmaf_rn(ddz, ddz, d);
+          d = h16(d);
+          if (d < 0.1f) continue;    // `d < 0.1` in double: no fp16 value lies in [0.1, 0.1f)
+        }
+        const uint2 rc = s.rec[nidx];
+        if (!(rc.y & RF_VALID)) {                                 // CK.py:229-235 carve the upper bound
+          const u32 key = fkey(nz);
+          if (key < rc.x && key < __ldcg(s.ukv + nidx)) {
+            red_min(s.ukv + nidx, key, s.mc_off);                 // true min over all rays (and ranks)
+            if (s.dirty) s.dirty[nidx] = 1;
+          }
+          continue;
+        }
+        if (rc.y & RF_T05) continue;                              // CK.py:237
+        const float nh = __uint_as_float(rc.x);
+        // CK.py:239 needs nh > nz + 0.01 - min(v,1)*0.05 >= nz - 0.04: reject far-below cells in fp32
+        if (nh < nz - 0.05f) continue;
+        const float nv = add_n_times(__ldg(map + C + nidx), c.c_out, (u32)(s.cnt_fo[nidx] >> 32));
+        const double rhs = fma(-fmin((double)nv, 1.0), 0.05, (double)nz + 0.01);   // CK.py:239 (nvcc contraction)
+        if (!((double)nh > rhs)) continue;
+        const float n0 = h16(__ldg(normal + nidx)), n1 = h16(__ldg(normal + C + nidx)), n2 = h16(__ldg(normal + 2 * C + nidx));
+        const float product = __fadd_rn(__fadd_rn(__fmul_rn(rx, n0), __fmul_rn(ry, n1)), __fmul_rn(rz, n2));   // CK.py:103-108
+        if ((double)fabsf(product) < c.cos_thresh) continue;      // CK.py:245
+        if ((rc.y & RF_WALL) && (rc.y & RF_T10)) continue;        // CK.py:246-247
+        const i64 dec_fix = fix32((float)(-c.cleanup_step / ((double)ra.w / c.max_ray_length)));   // CK.py:250
+        red_add((u64*)(s.DV + nidx), (u64)dec_fix, s.mc_off);     // CK.py:250
+        red_add(s.n_ray + nidx, 1u, s.mc_off);                    // CK.py:251
+        red_min(s.ukv + nidx, fkey(nz), s.mc_off);                // CK.py:253-256
+        if (s.dirty) s.dirty[nidx] = 1;
+      }
     }
-    r = __shfl_sync(0xffffffffu, pend, 0);
+   }
+    rbase = __shfl_sync(0xffffffffu, pend, 0);
   }
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -458,99 +648,140 @@ k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __res
 
 // Apply every side effect of the frame to the state planes, then average_map_kernel
 // (CK.py:362-384) and clear_overlap_map (EM.py:393-410); re-zero the consumed scratch.
-template <int V>
-__global__ void __launch_bounds__(256)
-k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const FrameScalars* __restrict__ fs,
-           const int rays_ran) {
-  // V consecutive cells per thread; the dense planes are read as vectors up front, the sparse
-  // accumulators (sums, keys) only for the cells that were touched.
-  pdl_trigger(); pdl_wait();
-  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * V;
-  if (i0 >= c.C) return;
+// One cell, full path: everything the frame may have done to it.
+__device__ __forceinline__ void finalize_cell(const DevCfg& c, float* __restrict__ map, const CellScratch& s, const int i,
+                                              const int rr, const int cc, const int applied, const float shift,
+                                              const float hmin, const float hmax, const int rays_ran) {
   const size_t C = (size_t)c.C;
-  float h0[V], v0[V], va0[V], ti0[V], up0[V], iu0[V];
-  ldv<V>(map + i0, h0); ldv<V>(map + C + i0, v0); ldv<V>(map + 2 * C + i0, va0);
-  ldv<V>(map + 4 * C + i0, ti0); ldv<V>(map + 5 * C + i0, up0); ldv<V>(map + 6 * C + i0, iu0);
-  u32 cf4[V], no4[V], nr4[V] = {}, ca4[V] = {}, rk4[V] = {}, kv4[V];
-  ldv<V>(s.cnt_fused + i0, cf4); ldv<V>(s.n_out + i0, no4);
-  for (int j = 0; j < V; j++) kv4[j] = UKEY_NONE;
-  if (rays_ran) {
-    ldv<V>(s.n_ray + i0, nr4); ldv<V>(s.ukv + i0, kv4);
-    if (V == 4) {
-      const uint4 R0 = reinterpret_cast<const uint4*>(s.rec + i0)[0], R1 = reinterpret_cast<const uint4*>(s.rec + i0)[1];
-      rk4[0] = R0.x; rk4[1 % V] = R0.z; rk4[2 % V] = R1.x; rk4[3 % V] = R1.z;
-    } else if (V == 2) {
-      const uint4 R0 = reinterpret_cast<const uint4*>(s.rec + i0)[0];
-      rk4[0] = R0.x; rk4[1 % V] = R0.z;
-    } else {
-      for (int j = 0; j < V; j++) rk4[j] = s.rec[i0 + j].x;
-    }
-  } else {
-    ldv<V>(s.cnt_all + i0, ca4);                                 // k_record did not run: re-zero the counts here
+  const u64 fo = s.cnt_fo[i], ca = s.cnt_ai[i];
+  const u32 cf = (u32)fo, no = (u32)(fo >> 32);
+  u32 nr = 0, kv = UKEY_NONE;
+  if (rays_ran) { nr = s.n_ray[i]; kv = s.ukv[i]; }
+  const float h0 = map[i], v0 = map[C + i], va0 = map[2 * C + i], ti0 = map[4 * C + i], up0 = map[5 * C + i], iu0 = map[6 * C + i];
+  float h = h0, v = v0, valid = va0, time = ti0, upper = up0, isup = iu0;
+  if (applied) h = __fadd_rn(h, shift);                           // EM.py:357 applied lazily
+  v = add_n_times(v, c.c_out, no);                                // CK.py:174
+  if (cf > 0) {                                                   // CK.py:187-192
+    valid = 1.f; time = 0.f; isup = 0.f;
+    upper = __uint_as_float((u32)(s.last[i] & 0xffffffffull));
   }
+  if (rays_ran) {
+    const u32 key0 = (isup < 0.5f) ? UKEY_NONE : fkey(upper);
+    if (nr > 0) {
+      valid = __fadd_rn(valid, (float)unfix32(s.DV[i]));          // CK.py:250
+      v = add_n_times(v, c.c_out, nr);                            // CK.py:251
+    }
+    // true min over rays (CK.py:230-233,253-256) of the keys carved into the cell
+    const u32 ukey = min(key0, kv);
+    if (ukey != key0) { upper = funkey(ukey); isup = 1.f; }
+  }
+  // average_map_kernel CK.py:362-384
+  const float valid_in = valid;
+  if (cf > 0) {
+    const double cnt = (double)cf;
+    const float mean_v = (float)(unfix32(s.SV[i]) / cnt);
+    if ((double)mean_v > c.max_variance) { h = 0.f; v = c.init_var; valid = 0.f; }
+    else { h = (float)(unfix32(s.SH[i]) / cnt); v = mean_v; valid = 1.f; }
+  }
+  if (valid_in < 0.5f) { h = 0.f; v = c.init_var; valid = 0.f; }
+  // clear_overlap_map EM.py:393-410
+  if (c.overlap && rr >= c.cell_min && rr < c.cell_max && cc >= c.cell_min && cc < c.cell_max) {
+    if (h < hmin || h > hmax) { h = 0.f; v = c.init_var; valid = 0.f; }
+    if (upper < hmin || upper > hmax) { upper = 0.f; isup = 0.f; }
+  }
+  if (applied || h != h0) map[i] = h;
+  if (v != v0) map[C + i] = v;
+  if (valid != va0) map[2 * C + i] = valid;
+  if (time != ti0) map[4 * C + i] = time;
+  if (upper != up0) map[5 * C + i] = upper;
+  if (isup != iu0) map[6 * C + i] = isup;
+  // re-zero the consumed scratch
+  if (cf) { s.SH[i] = 0; s.SV[i] = 0; s.last[i] = 0; }
+  if (fo) s.cnt_fo[i] = 0;
+  if (nr) { s.DV[i] = 0; s.n_ray[i] = 0; }
+  if (ca) s.cnt_ai[i] = 0;
+  if (kv != UKEY_NONE) s.ukv[i] = UKEY_NONE;
+}
+
+// V consecutive cells per thread.  A frame touches few cells (< 15 % at config B): the dirty marker (one byte per cell,
+// set by whichever kernel accumulated into the cell's scratch; in sharded frames derived from the all-reduced cnt_all / ukv)
+// selects the full path; everywhere else only the drift shift (EM.py:357) and the reset of invalid cells
+// (CK.py:380-384) remain: 3 planes read, at most 3 written, as vectors.  The cells that need the full path are
+// compacted per warp (shared-memory list) and then finalised one per LANE, so the rare path runs converged.
+template <int V>
+__global__ void __launch_bounds__(256, 4)
+k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const FrameScalars* __restrict__ fs,
+           const int rays_ran, int* __restrict__ ray_ctl, const int n_ctl) {
+  __shared__ int s_list[8][32 * V];
+  pdl_trigger(); pdl_wait();
+  if (blockIdx.x == 0) for (int k = threadIdx.x; k < n_ctl; k += blockDim.x) ray_ctl[k] = 0;   // consumed by k_raycast: next frame's
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+  const size_t C = (size_t)c.C;
   const int applied = fs->applied;
   const float shift = fs->shift;
-  float h4[V], v4[V], va4[V], ti4[V], up4[V], iu4[V];
-  const int r = i0 / c.W, col0 = i0 - r * c.W;
-  const float hmin = __fsub_rn(fs->overlap_tz, c.overlap_z_f), hmax = __fadd_rn(fs->overlap_tz, c.overlap_z_f);
-#pragma unroll
-  for (int j = 0; j < V; j++) {
-    const int i = i0 + j;
-    const u32 cf = cf4[j], no = no4[j], nr = nr4[j];
-    float h = h0[j], v = v0[j], valid = va0[j], time = ti0[j], upper = up0[j], isup = iu0[j];
-    if (applied) h = __fadd_rn(h, shift);
-    v = add_n_times(v, c.c_out, no);
-    if (cf > 0) {                                                 // CK.py:187-192
-      valid = 1.f; time = 0.f; isup = 0.f;
-      upper = __uint_as_float((u32)(s.last[i] & 0xffffffffull));
-    }
-    if (rays_ran) {
-      const float valid_pf = valid;                               // validity after the fusion stores
-      const u32 key0 = (isup < 0.5f) ? UKEY_NONE : fkey(upper);
-      if (nr > 0) {
-        valid = __fadd_rn(valid, (float)unfix32(s.DV[i]));        // CK.py:250
-        v = add_n_times(v, c.c_out, nr);                          // CK.py:251
+  u32 full = 0;                                                    // bit j: cell i0 + j takes the full path
+  int r = 0, col0 = 0;
+  if (i0 < c.C) {
+    r = i0 / c.W; col0 = i0 - r * c.W;                             // V == 4 only when W % 4 == 0: one row per thread
+    if (s.dirty) {
+      if (V == 4) {
+        const u32 d = *reinterpret_cast<const u32*>(s.dirty + i0);
+        if (d) {
+          *reinterpret_cast<u32*>(s.dirty + i0) = 0u;
+          full = ((d & 0xffu) ? 1u : 0u) | ((d & 0xff00u) ? 2u : 0u) | ((d & 0xff0000u) ? 4u : 0u) | ((d & 0xff000000u) ? 8u : 0u);
+        }
+      } else {
+        for (int j = 0; j < V; j++) if (s.dirty[i0 + j]) { full |= 1u << j; s.dirty[i0 + j] = 0; }
       }
-      // true min over rays (CK.py:230-233,253-256): invalid cells carry it in rec.x (single GPU) or ukv
-      // (sharded), valid cells in ukv
-      const u32 ukey = min((valid_pf < 0.5f) ? rk4[j] : key0, kv4[j]);
-      if (ukey != key0) { upper = funkey(ukey); isup = 1.f; }
+    } else {
+      u64 ca[V]; u32 kv[V];
+      ldv64<V>(s.cnt_ai + i0, ca); ldv<V>(s.ukv + i0, kv);
+      for (int j = 0; j < V; j++) if (ca[j] != 0ull || kv[j] != UKEY_NONE) full |= 1u << j;
     }
-    // average_map_kernel CK.py:362-384
-    const float valid_in = valid;
-    if (cf > 0) {
-      const double cnt = (double)cf;
-      const float mean_v = (float)(unfix32(s.SV[i]) / cnt);
-      if ((double)mean_v > c.max_variance) { h = 0.f; v = c.init_var; valid = 0.f; }
-      else { h = (float)(unfix32(s.SH[i]) / cnt); v = mean_v; valid = 1.f; }
+    if (c.overlap && r >= c.cell_min && r < c.cell_max)            // clear_overlap_map window (EM.py:393-410)
+      for (int j = 0; j < V; j++) if (col0 + j >= c.cell_min && col0 + j < c.cell_max) full |= 1u << j;
+    if (full != (1u << V) - 1u) {
+      float h0[V], v0[V], va0[V], h4[V], v4[V], va4[V];
+      ldv<V>(map + i0, h0); ldv<V>(map + C + i0, v0); ldv<V>(map + 2 * C + i0, va0);
+#pragma unroll
+      for (int j = 0; j < V; j++) {
+        const bool inval = va0[j] < 0.5f;                         // CK.py:380-384
+        h4[j] = inval ? 0.f : (applied ? __fadd_rn(h0[j], shift) : h0[j]);
+        v4[j] = inval ? c.init_var : v0[j];
+        va4[j] = inval ? 0.f : va0[j];
+      }
+      if (full == 0) {
+        if (applied || diffv<V>(h4, h0)) stv<V>(map + i0, h4);
+        if (diffv<V>(v4, v0)) stv<V>(map + C + i0, v4);
+        if (diffv<V>(va4, va0)) stv<V>(map + 2 * C + i0, va4);
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+          if ((full >> j) & 1u) continue;                         // finalised below by whichever lane picks it up
+          if (applied || h4[j] != h0[j]) map[i0 + j] = h4[j];
+          if (v4[j] != v0[j]) map[C + i0 + j] = v4[j];
+          if (va4[j] != va0[j]) map[2 * C + i0 + j] = va4[j];
+        }
+      }
     }
-    if (valid_in < 0.5f) { h = 0.f; v = c.init_var; valid = 0.f; }
-    // clear_overlap_map EM.py:393-410
-    int rr = r, cc = col0 + j;
-    if (cc >= c.W) { cc -= c.W; rr += 1; }
-    if (c.overlap && rr >= c.cell_min && rr < c.cell_max && cc >= c.cell_min && cc < c.cell_max) {
-      if (h < hmin || h > hmax) { h = 0.f; v = c.init_var; valid = 0.f; }
-      if (upper < hmin || upper > hmax) { upper = 0.f; isup = 0.f; }
-    }
-    h4[j] = h; v4[j] = v; va4[j] = valid; ti4[j] = time; up4[j] = upper; iu4[j] = isup;
-    // re-zero the sparse accumulators
-    if (cf) { s.SH[i] = 0; s.SV[i] = 0; s.last[i] = 0; }
-    if (nr) s.DV[i] = 0;
   }
-  if (applied || diffv<V>(h4, h0)) stv<V>(map + i0, h4);
-  if (diffv<V>(v4, v0)) stv<V>(map + C + i0, v4);
-  if (diffv<V>(va4, va0)) stv<V>(map + 2 * C + i0, va4);
-  if (diffv<V>(ti4, ti0)) stv<V>(map + 4 * C + i0, ti4);
-  if (diffv<V>(up4, up0)) stv<V>(map + 5 * C + i0, up4);
-  if (diffv<V>(iu4, iu0)) stv<V>(map + 6 * C + i0, iu4);
-  const u32 zero[V] = {};
-  if (anyv<V>(cf4)) stv<V>(s.cnt_fused + i0, zero);
-  if (anyv<V>(no4)) stv<V>(s.n_out + i0, zero);
-  if (anyv<V>(nr4)) stv<V>(s.n_ray + i0, zero);
-  if (anyv<V>(ca4)) { stv<V>(s.cnt_all + i0, zero); stv<V>(s.cnt_inl + i0, zero); }
-  bool kvd = false;
-  for (int j = 0; j < V; j++) kvd |= kv4[j] != UKEY_NONE;
-  if (kvd) { u32 none[V]; for (int j = 0; j < V; j++) none[j] = UKEY_NONE; stv<V>(s.ukv + i0, none); }
+  // warp-level compaction of the full-path cells
+  const int nfull = __popc(full);
+  int incl = nfull;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  int pos = incl - nfull;
+  for (int j = 0; j < V; j++) if ((full >> j) & 1u) s_list[wid][pos++] = i0 + j;
+  __syncwarp();
+  const float hmin = __fsub_rn(fs->overlap_tz, c.overlap_z_f), hmax = __fadd_rn(fs->overlap_tz, c.overlap_z_f);
+  for (int e = lane; e < total; e += 32) {
+    const int i = s_list[wid][e];
+    const int rr = i / c.W;
+    finalize_cell(c, map, s, i, rr, i - rr * c.W, applied, shift, hmin, hmax, rays_ran);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

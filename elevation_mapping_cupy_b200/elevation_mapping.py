@@ -114,6 +114,12 @@ class ElevationMap:
     def synchronize(self):
         self._check(self._L.emap_sync(self._h))
 
+    def set_stream(self, cuda_stream_handle):
+        """Run this handle's kernels on a caller-owned CUDA stream (int handle, e.g. torch.cuda.Stream().cuda_stream);
+        None / 0 restores the handle's own stream.  A frame fed from device memory is a fixed sequence of launches with
+        no host synchronisation, so it can be captured into a CUDA graph on that stream."""
+        self._check(self._L.emap_set_stream(self._h, C.c_void_p(int(cuda_stream_handle or 0))))
+
     def _ptr(self, name):
         p = C.c_void_p()
         self._check(self._L.emap_layer_device_ptr(self._h, name.encode(), C.byref(p)))
@@ -353,4 +359,6 @@ def _torch_sync():
     import sys
     torch = sys.modules.get("torch")
     if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+        if torch.cuda.is_current_stream_capturing():
+            return          # CUDA-graph capture: the caller runs the handle on the capturing stream (emap_set_stream)
         torch.cuda.current_stream().synchronize()

@@ -52,6 +52,17 @@ class PluginBase(ABC):
         return None
 
 
+class _MissingPlugin(PluginBase):
+    """Stands in for a plugin module that is not part of this package."""
+
+    def __init__(self, name):
+        super().__init__()
+        self.name = name
+
+    def __call__(self, elevation_map, layer_names, plugin_layers, plugin_layer_names, *args):
+        raise NotImplementedError(f"plugin {self.name!r} is not provided by this package")
+
+
 class PluginManager(object):
     def __init__(self, cell_n: int, engine=None, package: str = "elevation_mapping_cupy_b200.plugins"):
         self.cell_n = cell_n
@@ -68,7 +79,14 @@ class PluginManager(object):
         self.plugin_params = list(plugin_params)
         self.plugins = []
         for spec, extra in zip(plugin_params, extra_params):
-            module = importlib.import_module("." + spec.name, package=self.package)
+            try:
+                module = importlib.import_module("." + spec.name, package=self.package)
+            except ImportError as e:
+                # a YAML written for the reference may name a plugin this package does not provide (semantic / image
+                # plugins are outside the fusion path): keep the layer slot, say so, and fail only if it is evaluated
+                print(f"plugin {spec.name!r} is not provided by {self.package} ({e}); its layer will raise when requested")
+                self.plugins.append(_MissingPlugin(spec.name))
+                continue
             kwargs = dict(extra or {}, cell_n=self.cell_n, engine=self.engine)
             for cls_name, cls in inspect.getmembers(module, inspect.isclass):
                 if cls_name != "PluginBase" and issubclass(cls, PluginBase):

@@ -191,7 +191,13 @@ int emap_max_filter(emap_handle* h, const float* elevation, const float* is_vali
 int emap_erode(emap_handle* h, const float* layer, float* out, int32_t kernel_size, int32_t iterations, int32_t reverse);
 int emap_robot_centric_elevation(emap_handle* h, const float* elevation, const float* is_valid, const float R[9], float* out,
                                  double resolution, double threshold, int32_t use_threshold);
+/* plugins/inpainting.py:14-63 (Inpainting plugin; the reference runs cv2.inpaint on the HOST after a D2H copy): 8-bit
+ * normalisation over the valid cells, OpenCV's Telea fill with radius 1 of the cells with is_valid < 0.5,
+ * de-normalisation; all planes (W,W) fp32 on the device.  method 0 = telea (bit-identical to cv2.inpaint(..., 1,
+ * INPAINT_TELEA)); 'ns' is not implemented (EMAP_ERR_INVALID).  With no valid cell the layer is copied (inpainting.py:62). */
 int emap_inpaint(emap_handle* h, const float* elevation, const float* is_valid, float* out, int32_t method);
+/* diagnostics of the last emap_inpaint: fast-marching rounds, longest fixed-point iteration, rounds that hit the cap */
+int emap_inpaint_stats(emap_handle* h, int32_t* rounds, int32_t* max_jacobi, int32_t* not_converged);
 
 /* ---- plumbing ---- */
 int emap_sync(emap_handle* h);

@@ -622,6 +622,15 @@ void oracle_frame(const oracle_params* p, float* map, float* normal, float* trav
     free(SH); free(SV); free(DV); free(last); free(ukey); free(G); free(poses); free(sensor_of);
 }
 
+/* bench.py: torchrun exports OMP_NUM_THREADS=1; the CPU baselines must use every host core */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -416,7 +416,10 @@ def inpaint_cv2(elevation, is_valid, method="telea"):
     if (mask < 1).any():
         h = elevation
         h_max = float(h[mask < 1].max()); h_min = float(h[mask < 1].min())
-        h8 = ((elevation - h_min) * 255 / (h_max - h_min)).astype("uint8")
+        # CuPy's float32 -> uint8 conversion is CUDA's saturating cvt (NumPy's wraps): invalid cells outside the valid
+        # range only matter through cv2's shifted border reads, but keep the reference's (GPU) semantics
+        q = ((elevation.astype(np.float32) - np.float32(h_min)) * np.float32(255) / np.float32(h_max - h_min))
+        h8 = np.clip(np.nan_to_num(np.trunc(q), nan=0.0), 0, 255).astype("uint8")
         dst = np.array(cv.inpaint(h8, mask, 1, cv.INPAINT_NS if method == "ns" else cv.INPAINT_TELEA))
         return (dst.astype(np.float32) * (h_max - h_min) / 255 + h_min).astype(np.float64)
     return elevation
