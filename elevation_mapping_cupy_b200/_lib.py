@@ -46,6 +46,9 @@ SIGNATURES = {
     "emap_input_sensors": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int64,
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float]),
     "emap_get_point_record": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "emap_semantic_configure": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                          C.c_double]),
+    "emap_point_record_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "emap_get_frame_stats": (C.c_int, [C.c_void_p, C.POINTER(EmapFrameStats)]),
     "emap_set_ray_counting": (C.c_int, [C.c_void_p, C.c_int]),
     "emap_shard_begin": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int64,
@@ -64,6 +67,8 @@ SIGNATURES = {
     "emap_get_position": (C.c_int, [C.c_void_p, C.c_void_p]),
     "emap_get_map_with_name": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "emap_export_plane": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
+    "emap_get_layers": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                  C.c_void_p, C.c_int64]),
     "emap_layer_device_ptr": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "emap_exists_layer": (C.c_int, [C.c_void_p, C.c_char_p]),
     "emap_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -11,6 +11,7 @@
 #include "../../include/emap.h"
 #include "emap_kernels.cuh"
 #include "emap_inpaint.cuh"
+#include "emap_semantic.cuh"
 
 namespace {
 
@@ -82,10 +83,17 @@ struct emap_handle {
   bool zero_copy_pending = false;      // the index pass reads the caller's pinned host buffer: sync before returning
   // export staging
   float* d_export = nullptr;
+  size_t d_export_floats = 0;
   // plugin scratch
   float* pl[4] = {nullptr, nullptr, nullptr, nullptr};
   int* pl_cnt = nullptr;
   int pl_cnt_cap = 0;
+  // semantic point-channel fusion (emap_semantic_configure): caller-owned layers, library-owned per-frame sums
+  SemCfg sem{};
+  float* sem_map = nullptr;        // (n_layers, W, W) fp32, device, caller-owned
+  i64* sem_fsum = nullptr;         // one 2^-32 fixed-point sum plane per averaged channel
+  u32* sem_csum = nullptr;         // r, g, b, count planes per colour channel
+  int sem_fslots = 0, sem_cslots = 0;
   // inpainting scratch (allocated on first use): one block, carved into the arrays of InpaintView + lists + control
   void* ip_block = nullptr;
   size_t ip_bytes = 0;
@@ -362,6 +370,32 @@ int frame_fuse(emap_handle* h) {
   return 0;
 }
 
+// semantic point-channel fusion of the frame (semantic_map.py:223-259 after EM.py:369-371): needs the fused counts of
+// k_fuse and must run before k_finalize re-zeroes them
+template <typename T>
+int launch_sem_sum(emap_handle* h, const T* pts, i64 n, i64 stride, i64 off) {
+  if (n <= 0) return 0;
+  k_sem_sum<T><<<cdiv(n, 256), 256, 0, h->stream>>>(h->dc, h->sem, pts, n, stride, (const int*)(h->pidx + off), h->sem_fsum, h->sem_csum);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int frame_semantic(emap_handle* h) {
+  if (h->sem.n_ch <= 0 || !h->sem_map) return 0;
+  for (size_t s = 0; s < h->pend_pts.size(); s++) {
+    int rc = h->pend_dtype == EMAP_F32
+                 ? launch_sem_sum<float>(h, (const float*)h->pend_pts[s], h->pend_n[s], h->pend_stride, h->offs[s])
+                 : launch_sem_sum<double>(h, (const double*)h->pend_pts[s], h->pend_n[s], h->pend_stride, h->offs[s]);
+    if (rc) return rc;
+  }
+  // the cloud (staging buffer or the caller's pinned memory) is free only now
+  if (h->pend_host) CK(cudaEventRecord(h->in_free[h->in_sel ^ 1], h->stream));
+  if (h->zero_copy_pending) CK(cudaEventRecord(h->copy_done, h->stream));
+  k_sem_apply<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->sem, (const u64*)h->sc.cnt_fo, h->sem_fsum, h->sem_csum, h->sem_map);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // Cells a ray of this frame can reach.  A sample is t + ray*s with |ray| <= 1 per axis and s < len <= max_len16, so it
 // lies within max_len16 of the sensor on each axis; its fp16 rounding moves it by at most 2^-11 of its magnitude.
 // Rows [r0, r1) x columns [c0, c1), columns aligned to `align`; union over the frame's sensors, two cells of slack.
@@ -549,6 +583,7 @@ int emap_create(const emap_config* cfg, int device, emap_handle** out) {
   ALLOC(h->lut, sizeof(unsigned short) * 65536);
   ALLOC(h->tmap, sizeof(u32) * RT * RT);
   ALLOC(h->d_export, sizeof(float) * C);
+  h->d_export_floats = C;
   // march table as k_raycast reads it: [0] unused (lane 0 of the first warp iteration), [1 + k] = s_k, +inf padding up to
   // a whole number of 31-step warp iterations + one warp of over-read
   h->n_tab = (int)(((h->steps_host.size() + RC_STRIDE - 1) / RC_STRIDE) * RC_STRIDE + 64) & ~1;
@@ -627,7 +662,7 @@ int emap_destroy(emap_handle* h) {
   if (h->attached) { h->u32_block = nullptr; h->i64_block = nullptr; h->sc.last = nullptr; h->sc.rec = nullptr; h->sc.ukv = nullptr; h->fs = nullptr; }
   void* ptrs[] = {h->map, h->map_alt, h->normal, h->trav_input, h->u32_block, h->i64_block, h->sc.last, h->sc.rec,
                   h->sc.ukv, h->ukey_x, h->fs, h->steps, h->d_export, h->d_in[0], h->d_in[1], h->xyzv, h->pidx, h->pl[0], h->pl[1],
-                  h->pl[2], h->pl[3], h->pl_cnt, h->rays, h->ray_ctl, h->sc.thr, h->dirty, h->lut, h->tmap, h->ip_block};
+                  h->pl[2], h->pl[3], h->pl_cnt, h->rays, h->ray_ctl, h->sc.thr, h->dirty, h->lut, h->tmap, h->ip_block, h->sem_fsum, h->sem_csum};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int b = 0; b < 2; b++) if (h->in_free[b]) cudaEventDestroy(h->in_free[b]);
   if (h->copy_done) cudaEventDestroy(h->copy_done);
@@ -666,6 +701,7 @@ int emap_input_sensors(emap_handle* h, int32_t n_sensors, const void* const* poi
   if (rc) return rc;
   if ((rc = frame_index(h))) return rc;
   if ((rc = frame_fuse(h))) return rc;
+  if ((rc = frame_semantic(h))) return rc;
   if ((rc = frame_rays(h))) return rc;
   if ((rc = frame_finish(h))) return rc;
   if (!is_device_ptr || h->zero_copy_pending) CK(cudaEventSynchronize(h->copy_done));   // caller may reuse its host buffers on return
@@ -678,6 +714,53 @@ int emap_input_pointcloud(emap_handle* h, const void* points, int64_t n, int64_t
   const void* p[1] = {points};
   int64_t nn[1] = {n};
   return emap_input_sensors(h, 1, p, nn, row_stride, dtype, is_device_ptr, R, t, pn, on);
+}
+
+// ---- semantic point-channel fusion ------------------------------------------------------------
+int emap_semantic_configure(emap_handle* h, int32_t n_channels, const int32_t* column, const int32_t* kind, const int32_t* layer,
+                            float* semantic_map_device, int32_t n_layers, double average_weight) {
+  ENTER(h);
+  if (n_channels <= 0) { h->sem.n_ch = 0; h->sem_map = nullptr; return EMAP_OK; }
+  if (n_channels > SEM_MAX_CH || !column || !kind || !layer || !semantic_map_device || n_layers < 1)
+    return fail(h, EMAP_ERR_INVALID, "emap_semantic_configure: 1..16 channels, non-null arrays and layer buffer");
+  SemCfg c;
+  memset(&c, 0, sizeof(c));
+  c.n_ch = n_channels; c.alpha = average_weight;
+  int nf = 0, nc = 0;
+  for (int k = 0; k < n_channels; k++) {
+    if (column[k] < 3 || layer[k] < 0 || layer[k] >= n_layers || kind[k] < SEM_AVERAGE || kind[k] > SEM_COLOR)
+      return fail(h, EMAP_ERR_INVALID, "emap_semantic_configure: column >= 3, 0 <= layer < n_layers, kind 0..2 required");
+    c.col[k] = column[k]; c.kind[k] = kind[k]; c.layer[k] = layer[k];
+    c.slot[k] = (kind[k] == SEM_COLOR) ? 4 * nc++ : nf++;
+  }
+  const size_t C = (size_t)h->dc.C;
+  if (nf > h->sem_fslots) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->sem_fsum) cudaFree(h->sem_fsum);
+    h->sem_fsum = nullptr; h->sem_fslots = 0;
+    CK(cudaMalloc(&h->sem_fsum, sizeof(i64) * C * nf));
+    CK(cudaMemsetAsync(h->sem_fsum, 0, sizeof(i64) * C * nf, h->stream));
+    h->sem_fslots = nf;
+  }
+  if (nc > h->sem_cslots) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->sem_csum) cudaFree(h->sem_csum);
+    h->sem_csum = nullptr; h->sem_cslots = 0;
+    CK(cudaMalloc(&h->sem_csum, sizeof(u32) * C * 4 * nc));
+    CK(cudaMemsetAsync(h->sem_csum, 0, sizeof(u32) * C * 4 * nc, h->stream));
+    h->sem_cslots = nc;
+  }
+  h->sem = c; h->sem_map = semantic_map_device;
+  return EMAP_OK;
+}
+
+// device-resident write-back of the last frame (CK.py:260-262): packed (cell index | flags) per input row, see
+// PT_* in emap_device.cuh: bits 0..23 cell index, bit 28 valid, bit 29 inside, bit 30 row skipped (NaN)
+int emap_point_record_device_ptr(emap_handle* h, const int32_t** packed, int64_t* n) {
+  ENTER(h);
+  if (!packed || !n) return fail(h, EMAP_ERR_INVALID, "null argument");
+  *packed = (const int32_t*)h->pidx; *n = h->n_points;
+  return EMAP_OK;
 }
 
 // ---- sharded frame ---------------------------------------------------------------------------
@@ -837,7 +920,7 @@ static int shift_map(emap_handle* h, int sx, int sy, double dz) {
     LAUNCH_CHECK();
     return 0;
   }
-  k_shift<<<dim3(nb, 7), 256, 0, h->stream>>>(h->dc, h->map, h->map_alt, sx, sy, dz);
+  k_shift<<<nb, 256, 0, h->stream>>>(h->dc, h->map, h->map_alt, sx, sy, dz);
   LAUNCH_CHECK();
   float* t = h->map; h->map = h->map_alt; h->map_alt = t;
   return 0;
@@ -929,6 +1012,43 @@ int emap_export_plane(emap_handle* h, const float* plane, int fill_nan, int add_
                                                               (fill_nan ? 1 : 0) | (add_z ? 2 : 0));
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(out_host, h->d_export, sizeof(float) * Wo * Wo, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return EMAP_OK;
+}
+
+// Several layers in one launch, one device-to-host copy and one synchronisation (WRAP:213-252 get_grid_map exports a list
+// of layers per call).  names[k]: a basic layer name, or NULL / a plugin layer name together with planes[k] != NULL (a (W,W)
+// device plane, exported like emap_export_plane with flags[k]: bit 0 fill_nan, bit 1 add the centre height).
+int emap_get_layers(emap_handle* h, int32_t n, const char* const* names, const float* const* planes, const int32_t* flags,
+                    float* out_host, int64_t n_out_total) {
+  ENTER(h);
+  if (n < 1 || n > EXPORT_MAX_LAYERS || !out_host) return fail(h, EMAP_ERR_INVALID, "emap_get_layers: 1..24 layers, non-null output");
+  static const char* basic[] = {"elevation", "variance", "traversability", "time", "upper_bound", "is_upper_bound",
+                                "normal_x", "normal_y", "normal_z"};
+  const int Wo = h->dc.W - 2;
+  const size_t per = (size_t)Wo * Wo;
+  if (n_out_total != (int64_t)(per * n)) return fail(h, EMAP_ERR_INVALID, "output must hold n * (cell_n-2)^2 floats");
+  ExportList L;
+  memset(&L, 0, sizeof(L));
+  L.n = n;
+  for (int k = 0; k < n; k++) {
+    if (planes && planes[k]) { L.kind[k] = 9; L.plane[k] = planes[k]; L.flags[k] = flags ? flags[k] : 0; continue; }
+    int kind = -1;
+    if (names && names[k]) for (int i = 0; i < 9; i++) if (!strcmp(names[k], basic[i])) kind = i;
+    if (kind < 0) { h->err = std::string("Layer ") + (names && names[k] ? names[k] : "(null)") + " is not in the map"; return EMAP_ERR_NOLAYER; }
+    L.kind[k] = kind;
+  }
+  if (h->d_export_floats < per * n) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->d_export) cudaFree(h->d_export);
+    h->d_export = nullptr; h->d_export_floats = 0;
+    CK(cudaMalloc(&h->d_export, sizeof(float) * per * n));
+    h->d_export_floats = per * n;
+  }
+  k_export_multi<<<dim3(cdiv((i64)per, 256), n), 256, 0, h->stream>>>(h->dc, h->map, h->normal, h->d_export, L, h->center[2],
+                                                                       h->cfg.use_only_above_for_upper_bound);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(out_host, h->d_export, sizeof(float) * per * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return EMAP_OK;
 }
@@ -1090,8 +1210,9 @@ int emap_inpaint(emap_handle* h, const float* elevation, const float* is_valid, 
     CK(cudaMalloc(&h->ip_block, need));
     h->ip_bytes = need;
     int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_ip_march, 256, 0));
-    h->ip_grid = h->n_sm * std::max(1, std::min(nb, 2));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_ip_march, IP_MARCH_THREADS, 0));
+    if (nb < 1) return fail(h, EMAP_ERR_CUDA, "emap_inpaint: the cooperative kernel does not fit on an SM");
+    h->ip_grid = h->n_sm;          // one CTA per SM: the fronts are thin, and a grid barrier costs less with fewer CTAs
   }
   char* b = (char*)h->ip_block;
   InpaintView v;
@@ -1121,7 +1242,7 @@ int emap_inpaint(emap_handle* h, const float* elevation, const float* is_valid, 
   {
     int cap = 4096;
     void* args[] = {(void*)&v, (void*)&heapA, (void*)&heapB, (void*)&children, (void*)&ctl, (void*)&cap};
-    CK(cudaLaunchCooperativeKernel((const void*)k_ip_march, dim3(h->ip_grid), dim3(256), args, 0, h->stream));
+    CK(cudaLaunchCooperativeKernel((const void*)k_ip_march, dim3(h->ip_grid), dim3(IP_MARCH_THREADS), args, 0, h->stream));
     h->launches++;
   }
   k_ip_finish<<<nbC, 256, 0, h->stream>>>((int)C, (const uint8_t*)v.img, elevation, out, (const InpaintCtl*)ctl); LAUNCH_CHECK();

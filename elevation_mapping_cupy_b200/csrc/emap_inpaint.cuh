@@ -218,6 +218,102 @@ IP_HD bool ip_eval_child(const InpaintView& v, int c, int cur, float* t_out, uin
   return changed;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Same evaluation for a child at least 3 pixels away from the image border (none of the reference's shifted border
+// indices apply), written as GATHER-THEN-COMPUTE: the state of the 13 pixels within distance 2 is fetched with
+// independent loads (two waves: the pixels, then the poppers of those that are children of this round), so that a
+// device thread waits for a few memory round trips instead of a long chain of dependent ones.  Bit-identical to
+// ip_eval_child by construction (same operations in the same order); the host harness cross-checks both.
+//   stencil slots: 0 c | 1 up 2 left 3 right 4 down | 5 up-up 6 up-left 7 up-right 8 left-left 9 right-right
+//                  10 down-left 11 down-right 12 down-down
+IP_HD bool ip_interior(const InpaintView& v, int c) {
+  const int i = c / v.cols, j = c - i * v.cols;
+  return i >= 3 && j >= 3 && i <= v.rows - 4 && j <= v.cols - 4;
+}
+
+IP_HD bool ip_eval_child_fast(const InpaintView& v, int c, int cur, float* t_out, uint8_t* val_out) {
+  const int cols = v.cols, W = cols - 2;
+  const int off[13] = {0, -cols, -1, 1, cols, -2 * cols, -cols - 1, -cols + 1, -2, 2, cols - 1, cols + 1, 2 * cols};
+  uint8_t F[13], K[13], VC[13], IM[13];
+  float TT[13], TC[13];
+  const int ci = c / cols, cj = c - ci * cols;
+  const int cimg = (ci - 1) * W + (cj - 1);
+  const int offi[13] = {0, -W, -1, 1, W, -2 * W, -W - 1, -W + 1, -2, 2, W - 1, W + 1, 2 * W};
+#pragma unroll
+  for (int n = 0; n < 13; n++) {                                   // wave 1: independent loads
+    const int x = c + off[n];
+    F[n] = v.f[x]; K[n] = v.ck[x]; TT[n] = v.T[x]; TC[n] = v.Tc[cur][x]; VC[n] = v.vc[cur][x]; IM[n] = v.img[cimg + offi[n]];
+  }
+  int Q[13]; float TQ[13]; uint32_t OQ[13];
+#pragma unroll
+  for (int n = 0; n < 13; n++) {                                   // wave 2: poppers of the children among them
+    const bool ch = F[n] == IP_CHILD;
+    Q[n] = ch ? ip_popper(cols, c + off[n], K[n]) : c;
+    TQ[n] = v.T[Q[n]]; OQ[n] = v.ord[Q[n]];
+  }
+  bool kn[13]; float Tn[13]; int val[13];
+  kn[0] = false; Tn[0] = IP_TBIG; val[0] = IM[0];
+#pragma unroll
+  for (int n = 1; n < 13; n++) {
+    bool known = false, earlier = false;
+    if (F[n] == IP_KNOWN || F[n] == IP_BAND) known = true;
+    else if (F[n] == IP_CHILD) {
+      // ip_event_less(x, c)
+      if (Q[n] == Q[0]) earlier = K[n] < K[0];
+      else if (TQ[n] != TQ[0]) earlier = TQ[n] < TQ[0];
+      else if ((OQ[n] >> 3) != (OQ[0] >> 3)) earlier = (OQ[n] >> 3) < (OQ[0] >> 3);
+      else earlier = ip_key_less(v, Q[n], Q[0]);                   // rare: equal T and round, walk the popper chains
+    }
+    kn[n] = known || earlier;
+    Tn[n] = known ? TT[n] : (earlier ? TC[n] : IP_TBIG);
+    val[n] = earlier ? (int)VC[n] : (int)IM[n];
+  }
+  IpNb up, lf, rt, dn;
+  up.known = kn[1]; up.T = Tn[1]; lf.known = kn[2]; lf.T = Tn[2]; rt.known = kn[3]; rt.T = Tn[3]; dn.known = kn[4]; dn.T = Tn[4];
+  float dist = ip_solve(up, lf);
+  { const float d2 = ip_solve(dn, lf); if (d2 < dist) dist = d2; }
+  { const float d3 = ip_solve(up, rt); if (d3 < dist) dist = d3; }
+  { const float d4 = ip_solve(dn, rt); if (d4 < dist) dist = d4; }
+  float gtx, gty;
+  if (rt.known) gtx = lf.known ? IP_FMUL(IP_FSUB(rt.T, lf.T), 0.5f) : IP_FSUB(rt.T, dist);
+  else gtx = lf.known ? IP_FSUB(dist, lf.T) : 0.f;
+  if (dn.known) gty = up.known ? IP_FMUL(IP_FSUB(dn.T, up.T), 0.5f) : IP_FSUB(dn.T, dist);
+  else gty = up.known ? IP_FSUB(dist, up.T) : 0.f;
+  float Ia = 0.f, Jx = 0.f, Jy = 0.f, s = 1.0e-20f;
+  // per cross neighbour n (order up, left, right, down): slots of ITS left / right / up / down pixel, and r = c - n
+  const int nL[4] = {6, 8, 0, 10}, nR[4] = {7, 0, 9, 11}, nU[4] = {5, 6, 7, 0}, nD[4] = {0, 10, 11, 12};
+  const float rxs[4] = {0.f, 1.f, -1.f, 0.f}, rys[4] = {1.f, 0.f, 0.f, -1.f};
+#pragma unroll
+  for (int n = 0; n < 4; n++) {
+    const int sl = n + 1;
+    if (!kn[sl]) continue;
+    const float rx = rxs[n], ry = rys[n];
+    const float lev = (float)IP_DDIV(1.0, IP_DADD(1.0, fabs(IP_DSUB((double)Tn[sl], (double)dist))));
+    float dir = IP_FADD(IP_FMUL(rx, gtx), IP_FMUL(ry, gty));
+    if (fabs((double)dir) <= 0.01) dir = 0.000001f;
+    const float w = fabsf(IP_FMUL(lev, dir));
+    const bool r_kn = kn[nR[n]], l_kn = kn[nL[n]], d_kn = kn[nD[n]], u_kn = kn[nU[n]];
+    float gix, giy;
+    if (r_kn) gix = l_kn ? IP_FMUL((float)(val[nR[n]] - val[nL[n]]), 2.0f) : (float)(val[nR[n]] - val[sl]);
+    else gix = l_kn ? (float)(val[sl] - val[nL[n]]) : 0.f;
+    if (d_kn) giy = u_kn ? IP_FMUL((float)(val[nD[n]] - val[nU[n]]), 2.0f) : (float)(val[nD[n]] - val[sl]);
+    else giy = u_kn ? (float)(val[sl] - val[nU[n]]) : 0.f;
+    Ia = IP_FADD(Ia, IP_FMUL(w, (float)val[sl]));
+    Jx = IP_FSUB(Jx, IP_FMUL(w, IP_FMUL(gix, rx)));
+    Jy = IP_FSUB(Jy, IP_FMUL(w, IP_FMUL(giy, ry)));
+    s = IP_FADD(s, w);
+  }
+  const float jn = IP_FSQRT(IP_FADD(IP_FMUL(Jx, Jx), IP_FMUL(Jy, Jy)));
+  const float sat = IP_FADD(IP_FADD(IP_FDIV(Ia, s), IP_FDIV(IP_FADD(Jx, Jy), IP_FADD(jn, 1.0e-20f))), 0.5f);
+  int iv;
+  if (!(sat == sat)) iv = 0;
+  else { const float rn = rintf(sat < -1.0e6f ? -1.0e6f : (sat > 1.0e6f ? 1.0e6f : sat)); iv = (int)rn; }
+  iv = iv < 0 ? 0 : (iv > 255 ? 255 : iv);
+  const bool changed = (dist != TC[0]) || ((uint8_t)iv != VC[0]);
+  *t_out = dist; *val_out = (uint8_t)iv;
+  return changed;
+}
+
 // =============================================================================================
 #if defined(__CUDACC__)
 #include <cooperative_groups.h>
@@ -307,7 +403,8 @@ __device__ __forceinline__ bool ip_claim(uint8_t* f, int c) {
 }
 
 // The whole fast-marching replay: one cooperative launch, grid barriers between the passes of a round.
-__global__ void __launch_bounds__(256, 2)
+#define IP_MARCH_THREADS 512
+__global__ void __launch_bounds__(IP_MARCH_THREADS, 1)
 k_ip_march(InpaintView v, int* __restrict__ heapA, int* __restrict__ heapB, int* __restrict__ children, InpaintCtl* ctl,
            int jacobi_cap) {
   namespace cg = cooperative_groups;
@@ -348,7 +445,7 @@ k_ip_march(InpaintView v, int* __restrict__ heapA, int* __restrict__ heapB, int*
       for (int e = gtid; e < nchild; e += gsz) {
         const int c = children[e];
         float t; uint8_t val;
-        changed |= ip_eval_child(v, c, cur, &t, &val);
+        changed |= ip_interior(v, c) ? ip_eval_child_fast(v, c, cur, &t, &val) : ip_eval_child(v, c, cur, &t, &val);
         v.Tc[cur ^ 1][c] = t; v.vc[cur ^ 1][c] = val;
       }
       if (changed) atomicOr(&ctl->chg[it % 3], 1);
@@ -377,11 +474,8 @@ k_ip_march(InpaintView v, int* __restrict__ heapA, int* __restrict__ heapB, int*
       v.ord[c] = ((uint32_t)round << 3) | v.ck[c];
       hnext[atomicAdd(&ctl->heap_cnt[p ^ 1], 1)] = c;
       atomicMin(&ctl->tmin_bits[p ^ 1], __float_as_int(t));
+      v.f[c] = IP_BAND;            // byte store; nobody reads a child's state in this pass (in-round tests look at queue pixels)
     }
-    grid.sync();
-    // children become queue pixels only now: a popped pixel's in-round test above must not see them (it would not: their
-    // T is beyond the round, but f is also read by ip_claim's neighbours-of-word CAS in the next pass A)
-    for (int e = gtid; e < nchild; e += gsz) v.f[children[e]] = IP_BAND;
     if (gtid == 0) ctl->child_cnt = 0;
     grid.sync();
     p ^= 1;

@@ -1012,19 +1012,24 @@ k_normal(const DevCfg c, const float* __restrict__ dil, const float* __restrict_
 __global__ void __launch_bounds__(256)
 k_shift(const DevCfg c, const float* __restrict__ src, float* __restrict__ dst, int sx, int sy, double dz) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int layer = blockIdx.y;
   if (i >= c.C) return;
   const int W = c.W, r = i / W, cc = i - r * W;
+  const size_t C = (size_t)c.C;
   const bool pad = (sx > 0 && r < sx) || (sx < 0 && r >= W + sx) || (sy > 0 && cc < sy) || (sy < 0 && cc >= W + sy);
-  float v;
-  if (pad) v = (layer == L_V) ? c.init_var : 0.f;
-  else {
+  float v[7];
+  if (pad) {
+#pragma unroll
+    for (int l = 0; l < 7; l++) v[l] = (l == L_V) ? c.init_var : 0.f;
+  } else {
     int rs = r - sx, cs = cc - sy;
     rs = ((rs % W) + W) % W; cs = ((cs % W) + W) % W;
-    v = src[(size_t)layer * c.C + rs * W + cs];
+    const size_t si = (size_t)rs * W + cs;
+#pragma unroll
+    for (int l = 0; l < 7; l++) v[l] = __ldg(src + l * C + si);     // one index computation, seven loads in flight
   }
-  if (layer == L_H || layer == L_UPPER) v = (float)((double)v + dz);
-  dst[(size_t)layer * c.C + i] = v;
+  v[L_H] = (float)((double)v[L_H] + dz); v[L_UPPER] = (float)((double)v[L_UPPER] + dz);
+#pragma unroll
+  for (int l = 0; l < 7; l++) dst[l * C + i] = v[l];
 }
 __global__ void __launch_bounds__(256) k_shift_z(const DevCfg c, float* __restrict__ map, double dz) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1057,12 +1062,10 @@ __global__ void __launch_bounds__(256) k_update_time(const DevCfg c, float* __re
 // export EM.py:579-670,720-775: NaN-fill, +center_z, crop the border ring, flip both axes.
 // kind: 0 elevation, 1 variance, 2 traversability, 3 time, 4 upper_bound, 5 is_upper_bound, 6..8 normal xyz
 // kind 9: arbitrary plane with flags (bit0 fill_nan, bit1 add_z) = process_map_for_publish (EM.py:579-596)
-__global__ void __launch_bounds__(256)
-k_export(const DevCfg c, const float* __restrict__ map, const float* __restrict__ normal, float* __restrict__ out,
-         int kind, float center_z, int only_above, const float* __restrict__ plane, int flags) {
+__device__ __forceinline__ float export_value(const DevCfg& c, const float* __restrict__ map, const float* __restrict__ normal,
+                                              int o, int kind, float center_z, int only_above, const float* __restrict__ plane,
+                                              int flags) {
   const int Wo = c.W - 2;
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= Wo * Wo) return;
   const int orow = o / Wo, ocol = o - orow * Wo;
   const int r = Wo - 1 - orow + 1, cc = Wo - 1 - ocol + 1;         // flip(0), flip(1) of m[1:-1,1:-1]
   const int i = r * c.W + cc, C = c.C;
@@ -1086,7 +1089,29 @@ k_export(const DevCfg c, const float* __restrict__ map, const float* __restrict_
       break; }
     default: v = normal[(size_t)(kind - 6) * C + i]; break;
   }
-  out[o] = v;
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+k_export(const DevCfg c, const float* __restrict__ map, const float* __restrict__ normal, float* __restrict__ out,
+         int kind, float center_z, int only_above, const float* __restrict__ plane, int flags) {
+  const int Wo = c.W - 2;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= Wo * Wo) return;
+  out[o] = export_value(c, map, normal, o, kind, center_z, only_above, plane, flags);
+}
+
+// Several layers in one launch (WRAP:213-252 get_grid_map asks for a list of layers): blockIdx.y = layer.
+#define EXPORT_MAX_LAYERS 24
+struct ExportList { int n; int kind[EXPORT_MAX_LAYERS]; int flags[EXPORT_MAX_LAYERS]; const float* plane[EXPORT_MAX_LAYERS]; };
+__global__ void __launch_bounds__(256)
+k_export_multi(const DevCfg c, const float* __restrict__ map, const float* __restrict__ normal, float* __restrict__ out,
+               const ExportList L, float center_z, int only_above) {
+  const int Wo = c.W - 2;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = blockIdx.y;
+  if (o >= Wo * Wo) return;
+  out[(size_t)l * Wo * Wo + o] = export_value(c, map, normal, o, L.kind[l], center_z, only_above, L.plane[l], L.flags[l]);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -8,7 +8,8 @@ same method names, positional signatures and error behaviour, so the C++ bridge
 happens in the library; this module only marshals arguments.  Device arrays are handed out as torch
 CUDA tensors that alias the library's memory (they also expose `__cuda_array_interface__`).
 
-Out of scope: semantic layers, image input, polygon safety check, map initialiser.
+Point-cloud semantic layers (average / class_average / color fusion) are fused inside the frame (semantic_map.py).
+Out of scope: image input, image / bayesian semantic fusion, polygon safety check.
 """
 import ctypes as C
 import threading
@@ -19,6 +20,7 @@ import numpy as np
 from . import _lib
 from .parameter import Parameter
 from .plugins.plugin_manager import PluginManager
+from .semantic_map import SemanticMap
 
 LAYER_NAMES = ["elevation", "variance", "is_valid", "traversability", "time", "upper_bound", "is_upper_bound"]
 EXPORT_NAMES = ["elevation", "variance", "traversability", "time", "upper_bound", "is_upper_bound",
@@ -93,6 +95,7 @@ class ElevationMap:
         self.plugin_manager = PluginManager(cell_n=self.cell_n, engine=self)
         if param.plugin_config_file:
             self.plugin_manager.load_plugin_settings(param.plugin_config_file)
+        self.semantic_map = SemanticMap(param, engine=self)              # EM.py:106
         self.base_rotation = np.eye(3, dtype=np.float32)
         self._export_tmp = np.zeros((self.cell_n - 2, self.cell_n - 2), np.float32)
 
@@ -161,6 +164,7 @@ class ElevationMap:
     def clear(self):
         with self.map_lock:
             self._check(self._L.emap_clear(self._h))
+            self.semantic_map.clear()                              # EM.py:126
 
     def get_position(self, position):
         out = np.zeros(3, np.float64)
@@ -171,13 +175,24 @@ class ElevationMap:
         d = np.ascontiguousarray(np.asarray(delta_position, dtype=np.float64).reshape(3))
         with self.map_lock:
             self._check(self._L.emap_move(self._h, d.ctypes.data))
+            if self.semantic_map.layer_names:                     # EM.py:221 semantic layers move with the map
+                px = np.rint(d[:2] / self.resolution).astype(int)
+                self.synchronize()
+                self.semantic_map.shift_map_xy((int(px[0]), int(px[1])))
 
     def move_to(self, position, R):
         p = np.ascontiguousarray(np.asarray(position, dtype=np.float64).reshape(3))
         Rm = np.ascontiguousarray(_to_host(R), dtype=np.float32).reshape(9)
         self.base_rotation = Rm.reshape(3, 3).copy()
         with self.map_lock:
+            shift = None
+            if self.semantic_map.layer_names:                     # same cell shift as emap_move_to computes (EM.py:164-170)
+                px = np.rint((p[:2] - self.center[:2].astype(np.float64)) / self.resolution).astype(int)
+                shift = (-int(px[0]), -int(px[1]))
             self._check(self._L.emap_move_to(self._h, p.ctypes.data, Rm.ctypes.data))
+            if shift is not None:
+                self.synchronize()
+                self.semantic_map.shift_map_xy(shift)
 
     def update_variance(self):
         self._check(self._L.emap_update_variance(self._h))
@@ -199,7 +214,10 @@ class ElevationMap:
 
     def input_pointcloud(self, raw_points, channels: List[str], R, t, position_noise: float, orientation_noise: float):
         """EM.py:434-466.  raw_points: (N, 3+k) host (numpy / torch CPU, float32 or float64) or device
-        (torch CUDA / cupy) array; extra channels are ignored (semantic fusion is out of scope)."""
+        (torch CUDA / cupy) array.  Channels beyond x, y, z are fused into semantic layers inside the frame
+        (semantic_map.py:223-259; algorithms average / class_average / color)."""
+        if channels is not None and (len(channels) > 3 or self.semantic_map._configured is not None):
+            self.semantic_map.configure_for(list(channels))
         Rm = np.ascontiguousarray(_to_host(R), dtype=np.float32).reshape(9)
         tv = np.ascontiguousarray(_to_host(t), dtype=np.float32).reshape(3)
         dev = _device_pointer(raw_points)
@@ -270,12 +288,16 @@ class ElevationMap:
 
     def exists_layer(self, name):
         """EM.py:702-718"""
-        return name in self.layer_names or name in self.plugin_manager.layer_names
+        return (name in self.layer_names or name in self.semantic_map.layer_names
+                or name in self.plugin_manager.layer_names)
 
     def get_layer(self, name):
         """EM.py:807-835: the (W,W) device layer (torch CUDA tensor)."""
         if name in self.layer_names:
             return self.elevation_map[self.layer_names.index(name)]
+        if name in self.semantic_map.layer_names:
+            self.synchronize()
+            return self.semantic_map.semantic_map[self.semantic_map.layer_names.index(name)]
         if name in self.plugin_manager.layer_names:
             self._update_plugin(name)
             return self.plugin_manager.get_map_with_name(name)
@@ -283,8 +305,8 @@ class ElevationMap:
         return None
 
     def _update_plugin(self, name):
-        self.plugin_manager.update_with_name(name, self.elevation_map, self.layer_names, None, [],
-                                             self.base_rotation, {})
+        self.plugin_manager.update_with_name(name, self.elevation_map, self.layer_names, self.semantic_map.semantic_map,
+                                             self.semantic_map.layer_names, self.base_rotation, self.semantic_map.elements_to_shift)
 
     def get_map_with_name_ref(self, name, data):
         """EM.py:720-775: write layer `name` (NaN-filled, z-shifted, cropped, flipped) into `data`,
@@ -295,6 +317,11 @@ class ElevationMap:
         with self.map_lock:
             if name in EXPORT_NAMES:
                 self._check(self._L.emap_get_map_with_name(self._h, name.encode(), buf.ctypes.data, n_out))
+            elif name in self.semantic_map.layer_names:
+                # EM.py:747-748: semantic layers are exported as they are (cropped, flipped), no NaN fill, no z offset
+                m = self.semantic_map.semantic_map[self.semantic_map.layer_names.index(name)]
+                _torch_sync()
+                self._check(self._L.emap_export_plane(self._h, m.data_ptr(), 0, 0, buf.ctypes.data, n_out))
             elif name in self.plugin_manager.layer_names:
                 self._update_plugin(name)
                 m = self.plugin_manager.get_map_with_name(name)
@@ -305,6 +332,34 @@ class ElevationMap:
             else:
                 print("Layer {} is not in the map".format(name))
                 return
+        if not direct:
+            data[...] = buf.reshape(data.shape)
+
+    def get_maps_with_names_ref(self, names, data):
+        """Several layers at once (what the C++ bridge's get_grid_map does one by one, elevation_mapping_wrapper.cpp:213-252):
+        `data` is a caller-owned (len(names), cell_n-2, cell_n-2) float32 array.  One kernel, one D2H copy, one sync."""
+        n = len(names)
+        n_out = (self.cell_n - 2) ** 2
+        direct = isinstance(data, np.ndarray) and data.dtype == np.float32 and data.flags.c_contiguous and data.size == n * n_out
+        buf = data if direct else np.zeros((n, self.cell_n - 2, self.cell_n - 2), np.float32)
+        c_names = (C.c_char_p * n)(); planes = (C.c_void_p * n)(); flags = (C.c_int32 * n)()
+        keep = []
+        with self.map_lock:
+            for k, name in enumerate(names):
+                if name in EXPORT_NAMES:
+                    c_names[k] = name.encode(); planes[k] = None
+                elif name in self.plugin_manager.layer_names:
+                    self._update_plugin(name)
+                    m = self.plugin_manager.get_map_with_name(name)
+                    p = self.plugin_manager.get_param_with_name(name)
+                    keep.append(m)
+                    c_names[k] = name.encode(); planes[k] = m.data_ptr()
+                    flags[k] = int(bool(p.fill_nan)) | (int(bool(p.is_height_layer)) << 1)
+                else:
+                    raise KeyError("Layer {} is not in the map".format(name))
+            if keep:
+                _torch_sync()
+            self._check(self._L.emap_get_layers(self._h, n, c_names, planes, flags, buf.ctypes.data, n * n_out))
         if not direct:
             data[...] = buf.reshape(data.shape)
 

@@ -123,6 +123,18 @@ int emap_get_point_record(emap_handle* h, int32_t* idx, uint8_t* valid, uint8_t*
 int emap_get_frame_stats(emap_handle* h, emap_frame_stats* out);
 int emap_set_ray_counting(emap_handle* h, int enable);
 
+/* ---- semantic point-channel fusion: semantic_map.py:223-259 update_layers_pointcloud, called by
+ * EM.py:371 inside the frame.  Configure once (or whenever the channel set changes); every following
+ * emap_input_pointcloud / emap_input_sensors then also fuses the configured feature columns of the cloud into the caller's
+ * (n_layers, W, W) fp32 device buffer.  kind: 0 = fusion/pointcloud_average.py, 1 = fusion/pointcloud_class_average.py
+ * (average_weight = parameter.py:163), 2 = fusion/pointcloud_color.py (feature = packed 0x00RRGGBB bits in a float).
+ * n_channels = 0 switches it off.  Not applied to sharded frames. */
+int emap_semantic_configure(emap_handle* h, int32_t n_channels, const int32_t* column, const int32_t* kind,
+                            const int32_t* layer, float* semantic_map_device, int32_t n_layers, double average_weight);
+/* CK.py:260-262 write-back of the last frame, on the DEVICE: one packed int32 per input row (bits 0..23 cell index,
+ * bit 28 valid, bit 29 inside, bit 30 row dropped as NaN); valid until the next frame. */
+int emap_point_record_device_ptr(emap_handle* h, const int32_t** packed_device, int64_t* n);
+
 /* ---- sharded frame (one rank per GPU, replicated grid).  Between the phases the
  * caller all-reduces the exchange buffers in place (SUM for the int64/uint32 words named
  * "sum", MAX / MIN as named) with NCCL; single-GPU callers never need these. ---- */
@@ -169,6 +181,12 @@ int emap_get_map_with_name(emap_handle* h, const char* name, float* out_host, in
  * (W,W) fp32 device plane, then crop + flip + copy to the host. */
 int emap_export_plane(emap_handle* h, const float* plane_device, int fill_nan, int add_z, float* out_host,
                       int64_t n_out);
+/* Batched export: what WRAP:213-252 (ElevationMappingWrapper::get_grid_map) does layer by layer -- n layers with ONE
+ * kernel, one device-to-host copy, one synchronisation.  names[k] is a basic layer of emap_get_map_with_name, or
+ * planes[k] a (W,W) device plane (plugin layer) exported with flags[k] (bit 0: fill_nan, bit 1: add the centre height).
+ * out_host holds n consecutive (cell_n-2)^2 planes. */
+int emap_get_layers(emap_handle* h, int32_t n, const char* const* names, const float* const* planes_device,
+                    const int32_t* flags, float* out_host, int64_t n_out_total);
 /* EM.py:807-835 get_layer / raw state access: device pointer of a (W,W) fp32 plane.  Names: the 7
  * layers of EM.py:69-77, normal_x/y/z, traversability_input.  `elevation_map` returns the (7,W,W)
  * base, `normal_map` the (3,W,W) base.  Pointers stay valid until the next emap_move / emap_move_to / emap_destroy. */

@@ -36,6 +36,9 @@ REF_ROOT = "/root/reference/elevation_mapping_cupy/script/elevation_mapping_cupy
 OUT = os.path.join(HERE, "_ref")
 
 
+GENERATOR_VERSION = 2        # bump when the set of emitted kernels changes (prebuilt libraries are rebuilt)
+
+
 class _Rec:
     def __init__(self, in_params, out_params, operation, name, preamble=""):
         self.in_params, self.out_params = in_params, out_params
@@ -113,6 +116,27 @@ def _plugin_rec(fname, cls, attr, **ctor):
     return getattr(obj, attr)
 
 
+def _fusion_mod(fname):
+    """fusion/<fname>: module-level kernel factories; imports .fusion_manager (FusionBase) and cupy."""
+    src = open(os.path.join(REF_ROOT, "fusion", fname)).read()
+    src = src.replace("from .fusion_manager import FusionBase", "class FusionBase:\n    pass\n")
+    stub = types.ModuleType("cupy")
+    stub.ElementwiseKernel = lambda in_params, out_params, operation, name="k", preamble="", **kw: _Rec(
+        in_params, out_params, operation, name, preamble)
+    stub.ndarray = object
+    saved = sys.modules.get("cupy")
+    sys.modules["cupy"] = stub
+    try:
+        ns = {}
+        exec(compile(src, fname, "exec"), ns)
+    finally:
+        if saved is None:
+            sys.modules.pop("cupy", None)
+        else:
+            sys.modules["cupy"] = saved
+    return ns
+
+
 def _params(rec):
     """'raw U a, raw T b' -> [('U','a'), ...] for in and out."""
     def parse(s):
@@ -128,27 +152,36 @@ def _params(rec):
 CTYPE = {"U": "float", "T": "float", "int16": "short"}
 
 
-def _emit(rec, fn, gpu):
+def _emit(rec, fn, gpu, types=None, carray=False):
+    """types: C types of the kernel's other template letters (e.g. {"W": "int", "V": "unsigned int"}), as CuPy would
+    deduce them from the arrays the caller passes.  carray: wrap the raw pointers in CArr (float-indexable, as CuPy's
+    CArray is) inside the body."""
     ins, outs = _params(rec)
-    args = ["long long size"] + [f"const {CTYPE[t]}* {n}" for t, n in ins] + [f"{CTYPE[t]}* {n}" for t, n in outs]
+    CT = dict(CTYPE, **(types or {}))
+    sfx = "_" if carray else ""
+    args = ["long long size"] + [f"const {CT[t]}* {n}{sfx}" for t, n in ins] + [f"{CT[t]}* {n}{sfx}" for t, n in outs]
     names = [n for _, n in ins] + [n for _, n in outs]
-    body = rec.operation
+    wrap = ""
+    if carray:
+        wrap = "".join(f"const CArr<const {CT[t]}> {n}{{{n}_}}; " for t, n in ins) + "".join(f"const CArr<{CT[t]}> {n}{{{n}_}}; " for t, n in outs) + "\n"
+    extra_typedefs = "".join(f"typedef {c} {t}; " for t, c in (types or {}).items())
+    body = wrap + rec.operation
     if gpu:
-        s = f"namespace ns_{fn} {{\ntypedef float U; typedef float T;\n{rec.preamble}\n"
+        s = f"namespace ns_{fn} {{\ntypedef float U; typedef float T; {extra_typedefs}\n{rec.preamble}\n"
         s += f"__global__ void kern({', '.join(args)}) {{\n"
         s += "  for (long long i_ = blockIdx.x * (long long)blockDim.x + threadIdx.x; i_ < size; i_ += (long long)gridDim.x * blockDim.x) {\n"
         s += "    const int i = (int)i_;\n" + body + "\n  }\n}\n}\n"
         s += f'extern "C" int ref_{fn}({", ".join(args)}, void* stream) {{\n'
         s += "  if (size <= 0) return 0;\n"
-        s += f"  ns_{fn}::kern<<<(unsigned)((size + 127) / 128), 128, 0, (cudaStream_t)stream>>>(size, {', '.join(names)});\n"
+        s += f"  ns_{fn}::kern<<<(unsigned)((size + 127) / 128), 128, 0, (cudaStream_t)stream>>>(size, {', '.join(n + sfx for n in names)});\n"
         s += "  return (int)cudaGetLastError();\n}\n"
     else:
-        s = f"namespace refshim {{ namespace ns_{fn} {{\ntypedef float U; typedef float T;\n{rec.preamble}\n"
+        s = f"namespace refshim {{ namespace ns_{fn} {{\ntypedef float U; typedef float T; {extra_typedefs}\n{rec.preamble}\n"
         s += f"static inline void body(const int i, {', '.join(args[1:])}) {{\n{body}\n}}\n}} }}\n"
         s += f'extern "C" int ref_{fn}({", ".join(args)}, int parallel) {{\n'
         s += "  if (parallel) {\n    _Pragma(\"omp parallel for schedule(dynamic, 512)\")\n"
-        s += f"    for (long long i = 0; i < size; i++) refshim::ns_{fn}::body((int)i, {', '.join(names)});\n  }} else {{\n"
-        s += f"    for (long long i = 0; i < size; i++) refshim::ns_{fn}::body((int)i, {', '.join(names)});\n  }}\n  return 0;\n}}\n"
+        s += f"    for (long long i = 0; i < size; i++) refshim::ns_{fn}::body((int)i, {', '.join(n + sfx for n in names)});\n  }} else {{\n"
+        s += f"    for (long long i = 0; i < size; i++) refshim::ns_{fn}::body((int)i, {', '.join(n + sfx for n in names)});\n  }}\n  return 0;\n}}\n"
     return s
 
 
@@ -189,6 +222,18 @@ def generate(P, gpu):
     src = '#include "ref_shim.h"\n'
     for fn, rec in recs.items():
         src += _emit(rec, fn, gpu)
+    # semantic point-channel fusion (fusion/pointcloud_average.py, pointcloud_class_average.py, pointcloud_color.py)
+    avg = _fusion_mod("pointcloud_average.py"); cavg = _fusion_mod("pointcloud_class_average.py"); col = _fusion_mod("pointcloud_color.py")
+    alpha = P.get("average_weight", 0.5)
+    sem = {
+        "sem_sum": (avg["sum_kernel"](P["resolution"], W, W), {"W": "int"}),
+        "sem_average": (avg["average_kernel"](W, W), {"W": "int", "V": "float"}),
+        "sem_class_average": (cavg["class_average_kernel"](W, W, alpha), {"W": "int", "V": "float"}),
+        "sem_add_color": (col["add_color_kernel"](W, W), {"W": "int", "V": "unsigned int"}),
+        "sem_color_average": (col["color_average_kernel"](W, W), {"W": "int", "V": "unsigned int"}),
+    }
+    for fn, (rec, ty) in sem.items():
+        src += _emit(rec, fn, gpu, ty, carray=True)
     src += f'extern "C" int ref_cell_n(void) {{ return {W}; }}\n'
     return src
 
@@ -200,7 +245,8 @@ def build(P, tag=None, gpu=False, verbose=False):
     kind = "gpu" if gpu else "cpu"
     so = os.path.join(OUT, f"libref_{kind}_{tag}.so")
     meta = os.path.join(OUT, f"libref_{kind}_{tag}.json")
-    if os.path.exists(so) and os.path.exists(meta) and json.load(open(meta)) == P:
+    stamp = dict(P, _generator=GENERATOR_VERSION)
+    if os.path.exists(so) and os.path.exists(meta) and json.load(open(meta)) == stamp:
         return so
     if not os.path.isdir(REF_ROOT):
         raise FileNotFoundError(f"{REF_ROOT} absent and {so} not prebuilt")
@@ -218,7 +264,7 @@ def build(P, tag=None, gpu=False, verbose=False):
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
-    json.dump(P, open(meta, "w"), sort_keys=True)
+    json.dump(stamp, open(meta, "w"), sort_keys=True)
     return so
 
 

@@ -404,7 +404,7 @@ typedef struct {
 
 /* Layer order of `map` (7,W,W): elevation, variance, is_valid, traversability,
  * time, upper_bound, is_upper_bound (EM.py:69-77).  `normal` is (3,W,W).
- * `scratch_counts` (optional, 2*W*W floats) returns new_map[3], new_map[4]. */
+ * `scratch_counts` (optional, 3*W*W floats) returns new_map[3], new_map[4], new_map[2] (fused count). */
 void oracle_frame(const oracle_params* p, float* map, float* normal, float* trav_input,
                   const float* w1, const float* w2, const float* w3, const float* wout,
                   const float* pts, int64_t n, int64_t stride,
@@ -617,7 +617,7 @@ void oracle_frame(const oracle_params* p, float* map, float* normal, float* trav
     memset(normal, 0, sizeof(float) * 3 * C);
     oracle_normal(W, p->resolution, trav_input, VALID, normal);
 
-    if (scratch_counts) for (int i = 0; i < C; i++) { scratch_counts[i] = (float)cnt_inl[i]; scratch_counts[C + i] = (float)cnt_all[i]; }
+    if (scratch_counts) for (int i = 0; i < C; i++) { scratch_counts[i] = (float)cnt_inl[i]; scratch_counts[C + i] = (float)cnt_all[i]; scratch_counts[2 * C + i] = (float)cnt_fused[i]; }
     free(cnt_all); free(cnt_inl); free(cnt_fused); free(n_out); free(n_ray);
     free(SH); free(SV); free(DV); free(last); free(ukey); free(G); free(poses); free(sensor_of);
 }

@@ -301,7 +301,12 @@ class OracleElevationMap(_MapBase):
         super().__init__(param)
         self.nthreads = nthreads
         self.stats = None
-        self.counts = np.zeros((2, self.cell_n, self.cell_n), np.float32)
+        self.counts = np.zeros((3, self.cell_n, self.cell_n), np.float32)   # new_map[3], new_map[4], new_map[2]
+
+    @property
+    def counts_fused(self):
+        """new_map[2] of the last frame (CK.py:185): points fused per cell"""
+        return self.counts[2]
 
     def update_map_with_kernel(self, points_all, channels, R, t, position_noise, orientation_noise):
         self.input_sensors([points_all], [R], [t], position_noise, orientation_noise)
@@ -424,6 +429,45 @@ def inpaint_cv2(elevation, is_valid, method="telea"):
         return (dst.astype(np.float32) * (h_max - h_min) / 255 + h_min).astype(np.float64)
     return elevation
 
+
+
+# ---- semantic point-channel fusion ------------------------------------------------------------
+
+def semantic_fuse(W, idx, valid, inside, feats, kinds, semantic_map, cnt_fused, alpha=0.5):
+    """fusion/pointcloud_average.py:41-79, pointcloud_class_average.py, pointcloud_color.py:51-116 in NumPy, with the sums
+    accumulated in float64 (the reference's float atomics are order-dependent; this is the order-free value they
+    approximate).  idx/valid/inside: the write-back of CK.py:260-262; feats (N, k) float32; kinds: list of
+    'average' | 'class_average' | 'color' per column; semantic_map (k, W, W) float32 is updated in place; cnt_fused (W*W,)
+    = new_map[2] of the frame."""
+    C = W * W
+    sel = (valid > 0) & (inside > 0)
+    cells = idx[sel].astype(np.int64)
+    cnt = cnt_fused.reshape(-1).astype(np.float32)
+    for k, kind in enumerate(kinds):
+        layer = semantic_map[k].reshape(-1)
+        f = feats[sel, k].astype(np.float32)
+        if kind == "color":
+            col = f.view(np.uint32)
+            n = np.bincount(cells, minlength=C).astype(np.uint32)
+            r = np.bincount(cells, weights=((col >> 16) & 0xFF).astype(np.float64), minlength=C).astype(np.uint32)
+            g = np.bincount(cells, weights=((col >> 8) & 0xFF).astype(np.float64), minlength=C).astype(np.uint32)
+            b = np.bincount(cells, weights=(col & 0xFF).astype(np.float64), minlength=C).astype(np.uint32)
+            m = n > 0
+            rgb = ((r[m] // n[m]) << 16) + ((g[m] // n[m]) << 8) + (b[m] // n[m])
+            layer[m] = rgb.astype(np.uint32).view(np.float32)
+            continue
+        sums = np.bincount(cells, weights=f.astype(np.float64), minlength=C).astype(np.float32)
+        m = cnt > 0
+        if kind == "average":
+            layer[m] = sums[m] / (np.float32(1) * cnt[m])
+        else:
+            prev = layer.copy()
+            first = m & (prev == 0)
+            layer[first] = sums[first] / (np.float32(1) * cnt[first])
+            later = m & (prev != 0)
+            layer[later] = (alpha * prev[later].astype(np.float64)
+                            + (1 - alpha) * sums[later].astype(np.float64) / cnt[later].astype(np.float64)).astype(np.float32)
+    return semantic_map
 
 # ---- the reference's own kernel source, compiled for the host ------------------------------
 

@@ -18,6 +18,9 @@
 // ------------------------------------------------------------------ device flavour
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+// CuPy hands a `raw` argument to the kernel body as a CArray whose operator[] takes a ptrdiff_t: bodies that index with
+// a float (fusion/*.py: `U id = floorf(...); p[id * n]`) rely on the implicit float -> integer conversion.
+template <typename T> struct CArr { T* d; __device__ T& operator[](long long i) const { return d[i]; } };
 class float16 {
   __half data_;
  public:
@@ -41,6 +44,7 @@ __device__ inline float16 max(float16 x, float16 y) { return float16(fmaxf(float
 // ------------------------------------------------------------------ host flavour
 #include <cmath>
 #define __device__
+template <typename T> struct CArr { T* d; T& operator[](long long i) const { return d[i]; } };
 namespace refshim {
 class float16 {
   _Float16 data_;
@@ -91,5 +95,10 @@ inline float atomicAdd(float* addr, float val) {
   __builtin_memcpy(&f, &old, 4);
   return f;
 }
+// integer atomicAdd and the bit casts the colour fusion kernels use (fusion/pointcloud_color.py)
+inline unsigned int atomicAdd(unsigned int* addr, unsigned int val) { return __atomic_fetch_add(addr, val, __ATOMIC_RELAXED); }
+inline unsigned int atomicAdd(unsigned int* addr, int val) { return __atomic_fetch_add(addr, (unsigned int)val, __ATOMIC_RELAXED); }
+inline unsigned int __float_as_uint(float f) { unsigned int u; __builtin_memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned int u) { float f; __builtin_memcpy(&f, &u, 4); return f; }
 }  // namespace refshim
 #endif

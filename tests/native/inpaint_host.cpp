@@ -10,6 +10,8 @@
 
 extern "C" int inpaint_host(const uint8_t* img_in, const uint8_t* mask, int H, int W, uint8_t* out, int max_jacobi,
                             int* rounds_out, int* max_iters_out, int* not_converged_out, float* T_out, uint32_t* ord_out) {
+  const bool use_fast = max_jacobi >= 0;        // negative cap: generic evaluation only (cross-check of the two paths)
+  if (max_jacobi < 0) max_jacobi = -max_jacobi;
   const int rows = H + 2, cols = W + 2, N = rows * cols;
   std::vector<uint8_t> f(N, IP_KNOWN), ck(N, 0), vc0(N, 0), vc1(N, 0), img(img_in, img_in + (size_t)H * W);
   std::vector<float> T(N, IP_TBIG), Tc0(N, 0.f), Tc1(N, 0.f);
@@ -58,7 +60,8 @@ extern "C" int inpaint_host(const uint8_t* img_in, const uint8_t* mask, int H, i
       bool changed = false;
       for (int c : children) {
         float t; uint8_t val;
-        changed |= ip_eval_child(v, c, cur, &t, &val);
+        if (use_fast && ip_interior(v, c)) changed |= ip_eval_child_fast(v, c, cur, &t, &val);
+        else changed |= ip_eval_child(v, c, cur, &t, &val);
         v.Tc[cur ^ 1][c] = t; v.vc[cur ^ 1][c] = val;
       }
       cur ^= 1;

@@ -348,3 +348,78 @@ def test_feature_toggles_match_oracle(oracle_mod, flags):
             m.update_variance(); m.update_time()
         state, normal = em.get_state()
         compare_state(state, normal, om, label=f"{flags} frame {f}")
+
+
+def test_batched_export_equals_layer_by_layer(oracle_mod):
+    """emap_get_layers (one kernel, one D2H, one sync for N layers -- what the C++ bridge's get_grid_map asks for,
+    elevation_mapping_wrapper.cpp:213-252) against the single-layer export and the oracle, plugin layers included."""
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = core_parameter(202)
+    em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+    for f in range(2):
+        pts, R, t = wl.lidar_cloud(0, f, n_rings=32, n_az=625, max_range=8.0)
+        for m in (em, om):
+            m.move_to(t + np.float32(0.2), R)
+            m.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+    names = ["elevation", "variance", "traversability", "time", "upper_bound", "is_upper_bound", "normal_x", "normal_y",
+             "normal_z", "min_filter", "smooth"]
+    out = np.zeros((len(names), p.cell_n - 2, p.cell_n - 2), np.float32)
+    em.get_maps_with_names_ref(names, out)
+    one = np.zeros((p.cell_n - 2, p.cell_n - 2), np.float32)
+    for k, name in enumerate(names):
+        em.get_map_with_name_ref(name, one)
+        assert np.array_equal(out[k], one, equal_nan=True), name
+        if k < 9:
+            ref = om.export_layer(name)
+            tol = 2e-6 if name == "traversability" else 0.0
+            assert np.array_equal(np.isnan(out[k]), np.isnan(ref)), name
+            assert np.nanmax(np.abs(out[k] - ref), initial=0.0) <= tol, name
+    with pytest.raises(KeyError):
+        em.get_maps_with_names_ref(["no_such_layer"], out[:1])
+
+
+def test_semantic_point_fusion_matches_oracle(oracle_mod):
+    """feature channels of the cloud fused inside the frame (average / class_average / color) against the
+    oracle (pinned to the reference's fusion kernel strings on the CPU); exported through the reference's layer API."""
+    import torch
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    p = core_parameter(202)
+    p.pointcloud_channel_fusions = {"rgb": "color", "feat_avg": "average", "default": "class_average"}
+    em = _mk(p); om = oracle_mod.OracleElevationMap(p, nthreads=0)
+    W = 202
+    rng = np.random.default_rng(9)
+    sem_or = np.zeros((3, W, W), np.float32)
+    channels = ["x", "y", "z", "feat_avg", "person", "rgb"]
+    kinds = ["average", "class_average", "color"]
+    for f in range(3):
+        pts, R, t = wl.uniform_cloud(0, f, n=20000, half_extent=3.5)
+        feats = np.stack([rng.random(len(pts), dtype=np.float32) * 4 - 2, rng.random(len(pts), dtype=np.float32),
+                          rng.integers(0, 1 << 24, len(pts)).astype(np.uint32).view(np.float32)], 1)
+        cloud = np.ascontiguousarray(np.concatenate([pts, feats], 1))
+        # the oracle frame on xyz; fused counts = cells of points that the fusion accepted (new_map[2])
+        t_rel = (t - om.center).astype(np.float32)
+        idx, valid, inside, _ = oracle_mod.point_index(p, pts, R, t_rel)
+        src = torch.from_numpy(cloud).cuda() if f == 1 else cloud          # device rows once, host rows otherwise
+        em.input_pointcloud(src, channels, R, t, 0.02, 0.02)
+        om.input_pointcloud(pts, ["x", "y", "z"], R, t, 0.02, 0.02)
+        cnt = om.counts_fused.reshape(-1) if hasattr(om, "counts_fused") else None
+        if cnt is None:
+            pytest.skip("oracle does not expose the fused counts")
+        oracle_mod.semantic_fuse(W, idx, valid, inside, feats, kinds, sem_or, cnt, alpha=0.5)
+        got = np.stack([em.get_layer(n).cpu().numpy() for n in ("feat_avg", "person", "rgb")])
+        assert np.array_equal(got[2].view(np.uint32), sem_or[2].view(np.uint32)), f
+        for k in (0, 1):
+            assert np.abs(got[k] - sem_or[k]).max() <= 2e-6 * max(1.0, float(np.abs(sem_or[k]).max())), (f, kinds[k])
+    assert em.exists_layer("person") and em.exists_layer("rgb")
+    out = np.zeros((W - 2, W - 2), np.float32)
+    em.get_map_with_name_ref("person", out)
+    assert np.array_equal(out, np.flip(sem_or[1][1:-1, 1:-1], (0, 1)))
+    # the layers travel with the map (EM.py:221) and clear() empties them (EM.py:126)
+    em.move(np.array([0.08, -0.12, 0.0]))
+    moved = em.get_layer("person").cpu().numpy()
+    ref = np.roll(sem_or[1], (2, -3), (0, 1)); ref[:2, :] = 0; ref[:, -3:] = 0
+    assert np.array_equal(moved, ref)
+    em.clear()
+    assert float(em.get_layer("person").abs().max()) == 0.0

@@ -250,3 +250,50 @@ def test_flag_combinations_against_reference_source(oracle_mod, flags):
         assert np.array_equal(om.last_point_record[0], refs[0].last_point_record[0])
         assert n_cmp > 0.9 * 130 * 130
         om.update_variance(); om.update_time()
+
+
+def test_semantic_fusion_oracle_against_reference_source(oracle_mod):
+    """the NumPy restatement of the point-channel fusions (average, class_average, color) against the
+    reference's own kernel strings (fusion/pointcloud_average.py, pointcloud_class_average.py, pointcloud_color.py),
+    compiled for the host by oracle/build_ref.py and run one element at a time in input order."""
+    import ctypes as C
+    from oracle import build_ref
+    from oracle.configs import REF_CONFIGS
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    from elevation_mapping_cupy_b200 import workloads as wl
+    try:
+        L = C.CDLL(build_ref.build(REF_CONFIGS["core130"], tag="core130", gpu=False))
+        L.ref_sem_sum
+    except (FileNotFoundError, AttributeError):
+        pytest.skip("oracle/_ref (with the fusion kernels) not prebuilt and /root/reference absent")
+    p = core_parameter(130)
+    W = 130
+    rng = np.random.default_rng(3)
+    pts, R, t = wl.uniform_cloud(0, 1, n=6000, half_extent=2.3)
+    idx, valid, inside, _ = oracle_mod.point_index(p, pts, R, t)
+    feats = np.stack([rng.random(len(pts), dtype=np.float32) * 3, rng.random(len(pts), dtype=np.float32),
+                      rng.integers(0, 1 << 24, len(pts)).astype(np.uint32).view(np.float32)], 1)
+    kinds = ["average", "class_average", "color"]
+    pall = np.ascontiguousarray(np.concatenate([np.stack([idx, valid, inside], 1).astype(np.float32), feats], 1))
+    cnt = np.bincount(idx[(valid > 0) & (inside > 0)], minlength=W * W).astype(np.float32)
+    cnt[rng.random(W * W) < 0.3] = 0          # as if some cells' points had been rejected by the fusion (CK.py:174-179)
+    new_el = np.zeros((7, W, W), np.float32); new_el[2] = cnt.reshape(W, W)
+    fp = lambda a: a.ctypes.data_as(C.c_void_p)
+    dummy = np.zeros(16, np.float32)
+    sem_ref = np.zeros((3, W, W), np.float32); sem_or = np.zeros((3, W, W), np.float32)
+    for frame in range(2):                    # second frame exercises class_average's running mix
+        newmap = np.zeros((3, W, W), np.float32)
+        for k, kind in enumerate(kinds[:2]):
+            chan = np.array([3 + k], np.int32); lay = np.array([k], np.int32); dims = np.array([pall.shape[1], 1], np.int32)
+            L.ref_sem_sum(C.c_longlong(len(pts)), fp(pall), fp(dummy), fp(dummy), fp(chan), fp(lay), fp(dims), fp(sem_ref), fp(newmap), 0)
+            fn = L.ref_sem_average if kind == "average" else L.ref_sem_class_average
+            fn(C.c_longlong(W * W), fp(newmap), fp(chan), fp(lay), fp(dims), fp(new_el), fp(sem_ref), 0)
+        color_map = np.zeros((4, W, W), np.uint32)
+        chan = np.array([5], np.int32); lay = np.array([2], np.int32); dims = np.array([pall.shape[1], 1], np.int32)
+        L.ref_sem_add_color(C.c_longlong(len(pts)), fp(pall), fp(dummy), fp(dummy), fp(chan), fp(lay), fp(dims), fp(color_map), 0)
+        L.ref_sem_color_average(C.c_longlong(W * W), fp(color_map), fp(chan), fp(lay), fp(dims), fp(sem_ref), 0)
+        oracle_mod.semantic_fuse(W, idx, valid, inside, feats, kinds, sem_or, cnt, alpha=0.5)
+        assert np.array_equal(sem_ref[2].view(np.uint32), sem_or[2].view(np.uint32)), "color"
+        for k in (0, 1):
+            d = np.abs(sem_ref[k] - sem_or[k])
+            assert d.max() <= 2e-6 * max(1.0, float(np.abs(sem_ref[k]).max())), (frame, kinds[k], float(d.max()))
