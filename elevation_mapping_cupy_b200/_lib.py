@@ -58,12 +58,17 @@ SIGNATURES = {
     "emap_shard_set_overlap_z": (C.c_int, [C.c_void_p, C.c_float]),
     "emap_shard_exchange": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(EmapExchange), C.POINTER(C.c_int32)]),
     "emap_shard_phase": (C.c_int, [C.c_void_p, C.c_int32]),
+    "emap_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "emap_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "emap_input_sensors_sharded": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int64,
+                                             C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float]),
     "emap_move_to": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "emap_move": (C.c_int, [C.c_void_p, C.c_void_p]),
     "emap_clear": (C.c_int, [C.c_void_p]),
     "emap_update_variance": (C.c_int, [C.c_void_p]),
     "emap_update_time": (C.c_int, [C.c_void_p]),
     "emap_update_normal": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "emap_initialize_map_finish": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "emap_get_position": (C.c_int, [C.c_void_p, C.c_void_p]),
     "emap_get_map_with_name": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "emap_export_plane": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]),

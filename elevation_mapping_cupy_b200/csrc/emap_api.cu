@@ -8,6 +8,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/emap.h"
 #include "emap_kernels.cuh"
 #include "emap_inpaint.cuh"
@@ -88,6 +91,9 @@ struct emap_handle {
   float* pl[4] = {nullptr, nullptr, nullptr, nullptr};
   int* pl_cnt = nullptr;
   int pl_cnt_cap = 0;
+  // C-side communicator of sharded frames (emap_comm_init): NCCL, loaded at run time
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_nranks = 1;
   // semantic point-channel fusion (emap_semantic_configure): caller-owned layers, library-owned per-frame sums
   SemCfg sem{};
   float* sem_map = nullptr;        // (n_layers, W, W) fp32, device, caller-owned
@@ -236,6 +242,12 @@ int ensure_in(emap_handle* h, int b, size_t bytes) {
   return 0;
 }
 
+// NVTX range around the launches of one frame stage (visible in nsys / ncu timelines; a no-op without a tool attached)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 int stage_mark(emap_handle* h, int k) {
   if (!h->timing) return 0;
   CK(cudaEventRecord(h->st.ev[k], h->stream));
@@ -334,6 +346,7 @@ int frame_begin(emap_handle* h, int32_t n_sensors, const void* const* points, co
 
 // index + error-count pass of every sensor (CK.py:280-345)
 int frame_index(emap_handle* h) {
+  NvtxRange nv("emap:index+error");
   const int n_sensors = (int)h->pend_pts.size();
   for (int s = 0; s < n_sensors; s++) {
     int rc = h->pend_dtype == EMAP_F32
@@ -349,6 +362,7 @@ int frame_index(emap_handle* h) {
 }
 
 int frame_fuse(emap_handle* h) {
+  NvtxRange nv("emap:drift+fusion");
   PDL(k_drift, 1, 256, 0, h->dc, h->fs, h->pos_noise, h->ori_noise,
       h->overlap_override ? h->overlap_z_override : h->poses[0].t[2], 1, h->tmap);
   LAUNCH_CHECK();
@@ -382,6 +396,7 @@ int launch_sem_sum(emap_handle* h, const T* pts, i64 n, i64 stride, i64 off) {
 
 int frame_semantic(emap_handle* h) {
   if (h->sem.n_ch <= 0 || !h->sem_map) return 0;
+  NvtxRange nv("emap:semantic");
   for (size_t s = 0; s < h->pend_pts.size(); s++) {
     int rc = h->pend_dtype == EMAP_F32
                  ? launch_sem_sum<float>(h, (const float*)h->pend_pts[s], h->pend_n[s], h->pend_stride, h->offs[s])
@@ -427,6 +442,7 @@ RayGrid ray_grid(const emap_handle* h, int align) {
 }
 
 int frame_rays(emap_handle* h) {
+  NvtxRange nv("emap:record+raycast");
   const bool deferred = h->attached && h->n_points > 0;
   if (deferred) {   // sums + last-writer keys of the fusion: multicast pushes on the side stream, under the ray-cast
     CK(cudaEventRecord(h->ev_fork, h->stream));
@@ -487,6 +503,7 @@ int launch_post(emap_handle* h) {
 }
 
 int frame_finish(emap_handle* h) {
+  NvtxRange nv("emap:finalize+post");
   if (h->dc.W % 4 == 0) PDL(k_finalize<4>, cdiv(h->dc.C / 4, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility, h->ray_ctl, 2 * h->ray_ctl_cap);
   else PDL(k_finalize<1>, cdiv(h->dc.C, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility, h->ray_ctl, 2 * h->ray_ctl_cap);
   LAUNCH_CHECK();
@@ -654,11 +671,14 @@ int emap_create(const emap_config* cfg, int device, emap_handle** out) {
   return EMAP_OK;
 }
 
+static void comm_release(emap_handle* h);
+
 int emap_destroy(emap_handle* h) {
   if (!h) return EMAP_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  comm_release(h);
   if (h->attached) { h->u32_block = nullptr; h->i64_block = nullptr; h->sc.last = nullptr; h->sc.rec = nullptr; h->sc.ukv = nullptr; h->fs = nullptr; }
   void* ptrs[] = {h->map, h->map_alt, h->normal, h->trav_input, h->u32_block, h->i64_block, h->sc.last, h->sc.rec,
                   h->sc.ukv, h->ukey_x, h->fs, h->steps, h->d_export, h->d_in[0], h->d_in[1], h->xyzv, h->pidx, h->pl[0], h->pl[1],
@@ -882,6 +902,111 @@ int emap_shard_phase(emap_handle* h, int32_t phase) {
   return fail(h, EMAP_ERR_INVALID, "emap_shard_phase: phase must be 0..3");
 }
 
+// ---- sharded frames without a host framework: NCCL through the C ABI ---------------------------------------------
+// NCCL is loaded at run time (dlopen: no build- or load-time dependency); only the entry points and enum values used
+// below are declared, as nccl.h 2.x defines them.
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, emap_nccl_id, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok() const { return lib && GetUniqueId && CommInitRank && CommDestroy && AllReduce; }
+};
+NcclApi& nccl_api() {
+  static NcclApi a;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (a.lib) break; }
+    if (!a.lib) return;
+    a.GetUniqueId = (int (*)(void*))dlsym(a.lib, "ncclGetUniqueId");
+    a.CommInitRank = (int (*)(void**, int, emap_nccl_id, int))dlsym(a.lib, "ncclCommInitRank");
+    a.CommDestroy = (int (*)(void*))dlsym(a.lib, "ncclCommDestroy");
+    a.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(a.lib, "ncclAllReduce");
+    a.GetErrorString = (const char* (*)(int))dlsym(a.lib, "ncclGetErrorString");
+  });
+  return a;
+}
+enum { kNcclSum = 0, kNcclMax = 2, kNcclMin = 3, kNcclInt32 = 2, kNcclInt64 = 4 };
+}  // namespace
+
+static void comm_release(emap_handle* h) {
+  if (h->nccl_comm && nccl_api().ok()) { nccl_api().CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+}
+
+int emap_comm_unique_id(emap_nccl_id* out) {
+  if (!out) return EMAP_ERR_INVALID;
+  NcclApi& a = nccl_api();
+  if (!a.ok()) { g_create_error = "emap_comm_unique_id: libnccl.so.2 could not be loaded"; return EMAP_ERR_STATE; }
+  return a.GetUniqueId(out) == 0 ? EMAP_OK : EMAP_ERR_CUDA;
+}
+
+int emap_comm_init(emap_handle* h, const emap_nccl_id* id, int32_t rank, int32_t nranks) {
+  ENTER(h);
+  if (!id || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, EMAP_ERR_INVALID, "emap_comm_init: bad argument");
+  NcclApi& a = nccl_api();
+  if (!a.ok()) return fail(h, EMAP_ERR_STATE, "emap_comm_init: libnccl.so.2 could not be loaded");
+  if (h->nccl_comm) { a.CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+  const int r = a.CommInitRank(&h->nccl_comm, nranks, *id, rank);
+  if (r != 0) { h->err = std::string("ncclCommInitRank: ") + (a.GetErrorString ? a.GetErrorString(r) : "error"); h->nccl_comm = nullptr; return EMAP_ERR_CUDA; }
+  h->comm_rank = rank; h->comm_nranks = nranks;
+  return EMAP_OK;
+}
+
+static int comm_exchange(emap_handle* h, int phase) {
+  emap_exchange ex[4];
+  int32_t n = 4;
+  // (emap_shard_exchange takes the handle lock itself: this helper runs with it held, so build the list directly)
+  const i64 C = h->dc.C;
+  if (phase == 1) { ex[0] = {h->sc.cnt_ai, 2 * C, 3}; ex[1] = {&h->fs->E, 2, 0}; n = 2; }
+  else if (phase == 2) { ex[0] = {h->sc.SH, 2 * C, 0}; ex[1] = {h->sc.cnt_fo, 2 * C, 3}; ex[2] = {h->sc.last, C, 1}; n = 3; }
+  else {
+    if (!h->dc.visibility) return 0;
+    k_ukey_extract<<<cdiv(C, 256), 256, 0, h->stream>>>((int)C, h->sc.ukv, h->ukey_x);
+    LAUNCH_CHECK();
+    ex[0] = {h->sc.DV, C, 0}; ex[1] = {h->sc.n_ray, C, 3}; ex[2] = {h->ukey_x, C, 2}; n = 3;
+    h->phase = 4;
+  }
+  NcclApi& a = nccl_api();
+  for (int k = 0; k < n; k++) {
+    const int dt = (ex[k].kind == 0 || ex[k].kind == 1) ? kNcclInt64 : kNcclInt32;
+    const int op = ex[k].kind == 1 ? kNcclMax : ex[k].kind == 2 ? kNcclMin : kNcclSum;
+    const int r = a.AllReduce(ex[k].ptr, ex[k].ptr, (size_t)ex[k].count, dt, op, h->nccl_comm, h->stream);
+    if (r != 0) { h->err = std::string("ncclAllReduce: ") + (a.GetErrorString ? a.GetErrorString(r) : "error"); return EMAP_ERR_CUDA; }
+  }
+  return 0;
+}
+
+// One sharded frame, collective over the communicator of emap_comm_init: this rank's sensors are fused into the
+// replicated grid together with every other rank's (integer NCCL all-reduces between the phases; replicas stay bit-identical).
+int emap_input_sensors_sharded(emap_handle* h, int32_t n_sensors, const void* const* points, const int64_t* n, int64_t row_stride,
+                               int dtype, int is_device_ptr, const float* R, const float* t, int64_t global_point_offset,
+                               float overlap_sensor_z_absolute, float pn, float on) {
+  ENTER(h);
+  if (!h->nccl_comm) return fail(h, EMAP_ERR_STATE, "emap_input_sensors_sharded: call emap_comm_init first");
+  if (h->attached) return fail(h, EMAP_ERR_STATE, "handle is attached to a multicast scratch: use the emap_shard_* calls");
+  if (!points || !n || !R || !t) return fail(h, EMAP_ERR_INVALID, "emap_input_sensors_sharded: null argument");
+  int rc = frame_begin(h, n_sensors, points, n, row_stride, dtype, is_device_ptr, R, t, global_point_offset, pn, on, true);
+  if (rc) return rc;
+  if (!is_device_ptr && !h->zero_copy_pending) CK(cudaEventSynchronize(h->copy_done));
+  if ((rc = frame_index(h))) return rc;
+  if (h->zero_copy_pending) { CK(cudaEventSynchronize(h->copy_done)); h->zero_copy_pending = false; }
+  h->overlap_override = true; h->overlap_z_override = overlap_sensor_z_absolute - h->center[2];
+  if ((rc = comm_exchange(h, 1))) return rc;
+  if ((rc = frame_fuse(h))) return rc;
+  if ((rc = comm_exchange(h, 2))) return rc;
+  if ((rc = frame_rays(h))) return rc;
+  if ((rc = comm_exchange(h, 3))) return rc;
+  if (h->phase == 4) {
+    k_ukey_merge<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc.C, h->sc.ukv, h->ukey_x);
+    LAUNCH_CHECK();
+  }
+  return frame_finish(h);
+}
+
 // ---- read-backs ------------------------------------------------------------------------------
 int emap_get_point_record(emap_handle* h, int32_t* idx, uint8_t* valid, uint8_t* inside, int64_t n) {
   ENTER(h);
@@ -975,6 +1100,27 @@ int emap_update_normal(emap_handle* h, const float* dilated) {
   ENTER(h);
   k_normal<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, dilated ? dilated : h->trav_input, h->map + 2 * (size_t)h->dc.C, h->normal);
   LAUNCH_CHECK();
+  return EMAP_OK;
+}
+
+// EM.py:913-922: the device half of initialize_map, after the caller wrote the interpolated planes (emap_set_state):
+// `iterations` Jacobi passes of the initialiser dilation, then upper_bound <- elevation on valid cells.
+int emap_initialize_map_finish(emap_handle* h, int32_t dilation_size, int32_t iterations) {
+  ENTER(h);
+  if (dilation_size < 0 || dilation_size > 64 || iterations < 0 || iterations > 16)
+    return fail(h, EMAP_ERR_INVALID, "emap_initialize_map_finish: 0 <= dilation_size <= 64, 0 <= iterations <= 16");
+  int rc = alloc_plugin_scratch(h);
+  if (rc) return rc;
+  const size_t B = sizeof(float) * (size_t)h->dc.C;
+  const int nb = cdiv(h->dc.C, 256);
+  const int passes = dilation_size > 0 ? iterations : 0;
+  for (int it = 0; it < std::max(passes, 1); it++) {
+    CK(cudaMemcpyAsync(h->pl[0], h->map, B, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->pl[1], h->map + 2 * (size_t)h->dc.C, B, cudaMemcpyDeviceToDevice, h->stream));
+    k_init_dilate<<<nb, 256, 0, h->stream>>>(h->dc, h->pl[0], h->pl[1], h->map, passes ? dilation_size : 0,
+                                              it == std::max(passes, 1) - 1);
+    LAUNCH_CHECK();
+  }
   return EMAP_OK;
 }
 
@@ -1196,6 +1342,7 @@ int emap_smooth_filter(emap_handle* h, const float* in, float* out) {
 // fast-marching fill replayed on the device in parallel (emap_inpaint.cuh), bit-identical to cv2's result.
 int emap_inpaint(emap_handle* h, const float* elevation, const float* is_valid, float* out, int32_t method) {
   ENTER(h);
+  NvtxRange nv("emap:inpaint");
   if (!elevation || !is_valid || !out) return fail(h, EMAP_ERR_INVALID, "emap_inpaint: null argument");
   if (method != 0) return fail(h, EMAP_ERR_INVALID, "emap_inpaint: only method 0 (telea) is implemented; 'ns' (Navier-Stokes) is not");
   const int W = h->dc.W, rows = W + 2, cols = W + 2;

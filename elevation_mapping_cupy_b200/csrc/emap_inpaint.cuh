@@ -31,7 +31,8 @@ enum { IP_KNOWN = 0, IP_BAND = 1, IP_INSIDE = 2, IP_CHILD = 3 };
 #define IP_TBIG 1.0e6f
 #define IP_DELTA 0.70f            // round width in T; must stay below 1/sqrt(2)
 #define IP_ROOT 4                 // ord.k of an initial band pixel (no popper)
-#define IP_CMP_DEPTH 24
+#define IP_CMP_DEPTH 24            // popper-chain levels walked on a (T, round) tie before falling back to the pixel index;
+                                   // random images need the deep walk (a cap of 2 changes results), regular fronts tie all the way
 
 struct InpaintView {
   int rows, cols;                 // padded: image is (rows-2) x (cols-2), pixel (i,j) of the image = padded (i+1, j+1)

@@ -1058,6 +1058,32 @@ __global__ void __launch_bounds__(256) k_update_time(const DevCfg c, float* __re
   map[4 * c.C + i] = __fadd_rn(map[4 * c.C + i], c.time_int_f);
 }
 
+// EM.py:913-922 after the map initialiser: dilation_filter_kernel (CK.py:392-449) of the elevation into invalid cells with
+// mask = is_valid -- the reference runs it IN PLACE (racy); here every pass reads the previous pass's planes (src) and
+// writes the map -- and update_upper_bound_with_valid_elevation (EM.py:428-432) on the last pass.
+__global__ void __launch_bounds__(256)
+k_init_dilate(const DevCfg c, const float* __restrict__ src_h, const float* __restrict__ src_valid, float* __restrict__ map,
+              int k, int last) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.C) return;
+  const int W = c.W, C = c.C;
+  float h = src_h[i], valid = src_valid[i];
+  if (valid < 0.5f) {
+    float distance = 100.f, near_value = 0.f;
+    for (int dy = -k; dy <= k; dy++)
+      for (int dx = -k; dx <= k; dx++) {
+        const int idx = i + W * dy + dx;                          // flat index, as the reference (no row wrap handling)
+        if (idx < 0 || idx >= C) continue;
+        const int ix = idx / W, iy = idx - ix * W;
+        if (ix <= 0 || ix >= W - 1 || iy <= 0 || iy >= W - 1) continue;
+        if (src_valid[idx] > 0.5f && (float)(dx + dy) < distance) { distance = (float)(dx + dy); near_value = src_h[idx]; }
+      }
+    if (distance < 100.f) { h = near_value; valid = 1.0f; }
+  }
+  map[i] = h; map[2 * C + i] = valid;
+  if (last && valid > 0.5f) { map[5 * C + i] = h; map[6 * C + i] = 0.f; }     // EM.py:430-432
+}
+
 // ------------------------------------------------------------------------------------------
 // export EM.py:579-670,720-775: NaN-fill, +center_z, crop the border ring, flip both axes.
 // kind: 0 elevation, 1 variance, 2 traversability, 3 time, 4 upper_bound, 5 is_upper_bound, 6..8 normal xyz

@@ -388,15 +388,41 @@ class ElevationMap:
         self._check(self._L.emap_get_stage_ms(self._h, out.ctypes.data))
         return out
 
-    # ---- not on the fusion path ---------------------------------------------------------------
+    # ---- not on the per-frame path ---------------------------------------------------------------
     def input_image(self, *a, **k):
         raise NotImplementedError("image input is outside the fusion path (SURVEY.md section 8)")
 
     def get_polygon_traversability(self, *a, **k):
         raise NotImplementedError("polygon safety check is outside the fusion path (SURVEY.md section 8)")
 
-    def initialize_map(self, *a, **k):
-        raise NotImplementedError("map initialiser is outside the fusion path (SURVEY.md section 8)")
+    def initialize_map(self, points, method="cubic"):
+        """EM.py:899-922 + map_initializer.py:25-62: clear the map, interpolate the given (x, y, z) points (map frame) over
+        the grid with scipy.interpolate.griddata ON THE HOST -- exactly what the reference does (it copies to NumPy for
+        griddata) -- then, on the device, dilate twice with dilation_size_initialize and set upper_bound to the elevation
+        of the valid cells.  Start-up path, not on the per-frame path."""
+        from scipy.interpolate import griddata
+        self.clear()
+        pts = np.array(_to_host(points), dtype=np.float32, copy=True)
+        center = self.center
+        W = self.cell_n
+        # transform_to_map_index (traversability_polygon.py:61-63): truncation toward zero, like astype(int32)
+        idx = ((pts[:, :2] - center[:2].reshape(1, 2)) / np.float32(self.resolution) + W / 2).astype(np.int32)
+        pts[:, :2] = idx.astype(np.float32)
+        pts[:, 2] -= center[2]
+        state, normal = self.get_state()
+        vi = np.where(state[2] > 0.5)
+        points_idx = np.vstack([np.stack(vi).T.astype(np.float32), pts[:, :2]])
+        values = np.hstack([state[0][vi], pts[:, 2]])
+        assert points_idx.shape[0] > 3, "Initialization points must be more than 3."
+        gx, gy = np.mgrid[0:W, 0:W]
+        interp = griddata(points_idx, values, (gx, gy), method=method)
+        ok = ~np.isnan(interp)
+        state[0] = np.nan_to_num(interp).astype(np.float32)
+        state[1] = np.where(ok, np.float32(self.param.initialized_variance), np.float32(self.param.initial_variance))
+        state[2] = ok.astype(np.float32)
+        with self.map_lock:
+            self.set_state(state)
+            self._check(self._L.emap_initialize_map_finish(self._h, int(self.param.dilation_size_initialize), 2))
 
 
 def _to_host(x):

@@ -83,7 +83,7 @@ class SemanticMap:
             eng._check(eng._L.emap_semantic_configure(eng._h, 0, None, None, None, None, 0, 0.0))
             self._configured = key
             return
-        fusions = getattr(self.param, "pointcloud_channel_fusions", {"rgb": "color", "default": "class_average"})
+        fusions = getattr(self.param, "pointcloud_channel_fusions", None) or {"rgb": "color", "default": "class_average"}
         process, fusion = self.get_fusion(feats, fusions, self.layer_specs_points)
         cols, kinds, layers = [], [], []
         for ch, alg in zip(process, fusion):
@@ -94,6 +94,10 @@ class SemanticMap:
                 self.add_layer(ch)
             cols.append(3 + feats.index(ch)); kinds.append(KINDS[alg]); layers.append(self.layer_names.index(ch))
         n = len(cols)
+        if n == 0:                          # no channel has a fusion: nothing to fuse
+            eng._check(eng._L.emap_semantic_configure(eng._h, 0, None, None, None, None, 0, 0.0))
+            self._configured = key
+            return
         arr = lambda v: (C.c_int32 * n)(*v)
         eng._check(eng._L.emap_semantic_configure(eng._h, n, arr(cols), arr(kinds), arr(layers),
                                                   C.c_void_p(self.semantic_map.data_ptr()), len(self.layer_names),

@@ -161,6 +161,20 @@ int emap_shard_set_overlap_z(emap_handle* h, float sensor_z_absolute);
 int emap_shard_exchange(emap_handle* h, int32_t phase, emap_exchange* out, int32_t* n_out /*in: capacity*/);
 int emap_shard_phase(emap_handle* h, int32_t phase);   /* 0: index (attached handles only), 1: fusion, 2: ray-cast, 3: finalise+post */
 
+/* ---- sharded frames for a caller WITHOUT a host framework (SURVEY 8(b) emap_comm_init): NCCL through the C ABI.
+ * libnccl.so.2 is loaded at run time.  One rank obtains an id (emap_comm_unique_id == ncclGetUniqueId), distributes the
+ * 128 bytes by its own means, every rank calls emap_comm_init, and then every frame is ONE collective call:
+ * emap_input_sensors_sharded fuses this rank's sensors (arguments as emap_shard_begin) with all other ranks' into the
+ * replicated grid using integer NCCL all-reduces between the phases.  overlap_sensor_z_absolute: absolute z of the
+ * frame's FIRST sensor overall (the same value on every rank, see emap_shard_set_overlap_z). */
+typedef struct emap_nccl_id { char internal[128]; } emap_nccl_id;      /* == ncclUniqueId */
+int emap_comm_unique_id(emap_nccl_id* out);
+int emap_comm_init(emap_handle* h, const emap_nccl_id* id, int32_t rank, int32_t nranks);
+int emap_input_sensors_sharded(emap_handle* h, int32_t n_sensors, const void* const* points, const int64_t* n,
+                               int64_t row_stride, int dtype, int is_device_ptr, const float* R, const float* t,
+                               int64_t global_point_offset, float overlap_sensor_z_absolute, float position_noise,
+                               float orientation_noise);
+
 /* ---- pose / time: EM.py:139-170 move, move_to (WRAP:180-186); EM.py:119-128 clear (WRAP:188-191);
  * EM.py:420-426 update_variance, update_time (WRAP:193-203) ---- */
 int emap_move_to(emap_handle* h, const double position[3], const float R[9]);
@@ -171,6 +185,11 @@ int emap_update_time(emap_handle* h);
 /* EM.py:564-577 update_normal(dilated_map): device pointer to a (W,W) fp32 plane, or NULL for
  * the engine's own traversability_input. */
 int emap_update_normal(emap_handle* h, const float* dilated_map_device);
+/* EM.py:899-922 initialize_map, device half: after the caller has written the interpolated elevation / variance /
+ * is_valid planes (emap_set_state; the interpolation itself is SciPy's griddata on the host in the reference too,
+ * map_initializer.py:25-62), run `iterations` passes of the initialiser's dilation (CK.py:392-449 with
+ * dilation_size_initialize, mask = is_valid) and update_upper_bound_with_valid_elevation (EM.py:428-432). */
+int emap_initialize_map_finish(emap_handle* h, int32_t dilation_size_initialize, int32_t iterations);
 int emap_get_position(emap_handle* h, double out[3]);          /* EM.py:130-137 */
 
 /* ---- export: EM.py:720-775 get_map_with_name_ref (WRAP:205-252): NaN-fill, +center_z, crop the

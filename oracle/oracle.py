@@ -469,6 +469,52 @@ def semantic_fuse(W, idx, valid, inside, feats, kinds, semantic_map, cnt_fused, 
                             + (1 - alpha) * sums[later].astype(np.float64) / cnt[later].astype(np.float64)).astype(np.float32)
     return semantic_map
 
+
+# ---- map initialiser: EM.py:899-922, map_initializer.py:25-62 ----------------------------------
+
+def initialize_map_planes(param, state, points, center, method="cubic"):
+    """NumPy restatement of initialize_map on a cleared map: griddata interpolation of `points` (x, y, z in the map frame),
+    two Jacobi passes of dilation_filter_kernel (CK.py:392-449, dilation_size_initialize, mask = is_valid; the reference runs
+    them in place) and update_upper_bound_with_valid_elevation (EM.py:428-432).  Returns the (7,W,W) state."""
+    from scipy.interpolate import griddata
+    W = param.cell_n
+    st = state.copy()
+    pts = np.array(points, np.float32, copy=True)
+    idx = ((pts[:, :2] - np.asarray(center, np.float32)[:2].reshape(1, 2)) / np.float32(param.resolution) + W / 2).astype(np.int32)
+    pts[:, :2] = idx.astype(np.float32); pts[:, 2] -= np.float32(center[2])
+    vi = np.where(st[2] > 0.5)
+    pidx = np.vstack([np.stack(vi).T.astype(np.float32), pts[:, :2]])
+    vals = np.hstack([st[0][vi], pts[:, 2]])
+    gx, gy = np.mgrid[0:W, 0:W]
+    interp = griddata(pidx, vals, (gx, gy), method=method)
+    ok = ~np.isnan(interp)
+    st[0] = np.nan_to_num(interp).astype(np.float32)
+    st[1] = np.where(ok, np.float32(param.initialized_variance), np.float32(param.initial_variance))
+    st[2] = ok.astype(np.float32)
+    k = int(param.dilation_size_initialize)
+    for it in range(2 if k > 0 else 0):
+        h, m = st[0].reshape(-1).copy(), st[2].reshape(-1).copy()
+        nh, nm = h.copy(), m.copy()
+        C = W * W
+        for i in np.nonzero(m < 0.5)[0]:
+            dist, near = 100.0, 0.0
+            for dy in range(-k, k + 1):
+                for dx in range(-k, k + 1):
+                    j = i + W * dy + dx
+                    if j < 0 or j >= C:
+                        continue
+                    ix, iy = divmod(j, W)
+                    if ix <= 0 or ix >= W - 1 or iy <= 0 or iy >= W - 1:
+                        continue
+                    if m[j] > 0.5 and dx + dy < dist:
+                        dist, near = dx + dy, h[j]
+            if dist < 100:
+                nh[i], nm[i] = near, 1.0
+        st[0], st[2] = nh.reshape(W, W), nm.reshape(W, W)
+    mask = st[2] > 0.5
+    st[5] = np.where(mask, st[0], st[5]); st[6] = np.where(mask, 0.0, st[6])
+    return st
+
 # ---- the reference's own kernel source, compiled for the host ------------------------------
 
 class RefKernelMap(_MapBase):

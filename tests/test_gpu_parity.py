@@ -423,3 +423,20 @@ def test_semantic_point_fusion_matches_oracle(oracle_mod):
     assert np.array_equal(moved, ref)
     em.clear()
     assert float(em.get_layer("person").abs().max()) == 0.0
+
+
+def test_initialize_map_matches_oracle(oracle_mod):
+    """EM.py:899-922: griddata on the host (as the reference), dilation x2 + upper-bound fill on the device."""
+    from elevation_mapping_cupy_b200.parameter import core_parameter
+    p = core_parameter(64, dilation_size_initialize=3)
+    em = _mk(p)
+    em.move_to(np.array([0.4, -0.2, 0.3]), np.eye(3, dtype=np.float32))
+    pts = np.array([[0.0, 0.2, 0.31], [0.9, -0.6, 0.42], [-0.3, -0.9, 0.2], [0.1, 0.5, 0.55], [0.8, 0.3, 0.4]], np.float32)
+    before, _ = em.get_state()
+    em.initialize_map(pts, "linear")
+    state, _ = em.get_state()
+    cleared = np.zeros_like(before); cleared[1] = np.float32(p.initial_variance)      # clear() first (EM.py:905)
+    ref = oracle_mod.initialize_map_planes(p, cleared, pts, em.center, "linear")
+    assert (state[2] > 0.5).sum() > 50
+    for li in (0, 1, 2, 5, 6):
+        assert np.array_equal(state[li], ref[li]), li

@@ -54,6 +54,7 @@ def test_state_matches_reference_gpu_kernels_on_order_independent_cells():
     em = _mk(p); refs = [_ref(p, "core256") for _ in range(3)]
     rng = np.random.default_rng(4)
     worst = 0.0
+    worst_trav = 0.0
     for f in range(5):
         pts, R, t = wl.lidar_cloud(0, f, n_rings=32, n_az=625, max_range=8.0)
         em.move_to(t, R)
@@ -76,6 +77,20 @@ def test_state_matches_reference_gpu_kernels_on_order_independent_cells():
                 racy |= np.abs(outs[0][li] - o[li]) > 1e-6
         assert racy.mean() < 0.06, racy.mean()
         n_cmp = int((~racy).sum())
+        # traversability (layer 3): the reference computes it with torch / cuDNN convolutions (traversability_filter.py:
+        # 15-42, TF32 off); it depends on the dilated upper bound within a 13 x 13 window, so compare where no racy or
+        # upper-bound-unstable cell lies in that window
+        ub_ok = ~racy
+        for o in outs[1:]:
+            ub_ok &= (np.abs(outs[0][5] - o[5]) <= 1e-6) & (outs[0][6] == o[6])
+        ub_ok &= (np.abs(state[5] - outs[0][5]) <= 1e-6) & (state[6] == outs[0][6])
+        from scipy import ndimage
+        clean = ndimage.minimum_filter(ub_ok.astype(np.uint8), size=13, mode="constant", cval=0).astype(bool)
+        clean[:3, :] = clean[-3:, :] = False; clean[:, :3] = clean[:, -3:] = False
+        if clean.sum() > 100:
+            dt = np.abs(state[3] - outs[0][3])[clean]
+            assert float(dt.max()) <= 1e-4, (f, "traversability vs cuDNN", float(dt.max()), int(clean.sum()))
+            worst_trav = max(worst_trav, float(dt.max()))
         for li in (0, 1, 2, 4):
             d = np.abs(state[li] - outs[0][li])[~racy]
             bad = int((d > 1e-4).sum())
@@ -95,7 +110,8 @@ def test_state_matches_reference_gpu_kernels_on_order_independent_cells():
         # (upper_bound of a cell fused by several points is the new_h of an ARBITRARY one of them in the reference,
         # CK.py:191; the engine takes the last in input order -- not comparable cell by cell)
         em.update_variance(); em.update_time()
-    print("largest abs difference vs reference GPU kernels over the accepted order-independent cells:", worst)
+    print("largest abs difference vs reference GPU kernels over the accepted order-independent cells:", worst,
+          "; traversability vs the cuDNN path:", worst_trav)
 
 
 def test_reference_gpu_kernels_timing_config_b():
