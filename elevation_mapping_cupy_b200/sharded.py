@@ -159,7 +159,10 @@ class ShardedElevationMap:
                 if a.dtype not in (np.float32, np.float64):
                     a = a.astype(np.float32)
                 ptr, n, row, d, k = a.ctypes.data, a.shape[0], a.shape[1], (_lib.EMAP_F32 if a.dtype == np.float32 else _lib.EMAP_F64), a
-            stride, dt = (row, d) if stride is None else (stride, dt)
+            if stride is None:
+                stride, dt = row, d
+            elif (row, d) != (stride, dt):           # same check as ElevationMap.input_sensors
+                raise ValueError("all clouds of one frame must share dtype and column count")
             keep.append(k); ptrs[i] = ptr; counts[i] = n
         total_local = sum(int(c) for c in counts)
         off, _total = self.static_offsets if self.static_offsets else global_point_offsets(total_local, self.group)
