@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libemap.so")
+# EMAP_LIB selects an experimental build variant (tools/ A/B runs); the product is libemap.so
+LIB_PATH = os.environ.get("EMAP_LIB") or os.path.join(PKG, "libemap.so")
 
 EMAP_ABI_VERSION = 1
 EMAP_F32, EMAP_F64 = 0, 1

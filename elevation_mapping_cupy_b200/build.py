@@ -6,7 +6,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libemap.so")
 SOURCES = ["emap_api.cu"]
-HEADERS = ["emap_kernels.cuh", "emap_device.cuh", os.path.join("..", "..", "include", "emap.h")]
+HEADERS = ["emap_kernels.cuh", "emap_device.cuh", "emap_inpaint.cuh", "emap_semantic.cuh", os.path.join("..", "..", "include", "emap.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "-Xptxas", "-v"]
 
@@ -32,6 +32,17 @@ def build(force=False, verbose=False):
     with open(os.path.join(PKG, "libemap.ptxas.log"), "w") as f:
         f.write(r.stderr)
     return LIB
+
+
+def build_variant(name, defines):
+    """Experimental build with extra -D flags into libemap_<name>.so (selected at run time with EMAP_LIB=...)."""
+    out = os.path.join(PKG, "libemap_%s.so" % name)
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        print(r.stderr)
+        raise RuntimeError("nvcc failed building " + out)
+    return out
 
 
 if __name__ == "__main__":

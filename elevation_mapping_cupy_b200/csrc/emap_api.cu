@@ -52,6 +52,7 @@ struct emap_handle {
   int n_tab = 0;
   std::vector<float> steps_host;
   unsigned short* lut = nullptr;   // cell of every fp16 bit pattern (k_build_lut)
+  unsigned short* step_cnt = nullptr;   // march steps below every non-negative fp16 value (k_build_step_cnt)
   unsigned char* dirty = nullptr;  // per-cell dirty bytes of single-GPU frames (CellScratch::dirty)
   u32* tmap = nullptr;             // coarse ray map of the frame: RT x RT tile maxima of thr (keys)
   size_t rc_smem = 0;
@@ -258,7 +259,7 @@ template <typename T>
 int launch_index(emap_handle* h, const Pose& q, const T* pts, i64 n, i64 stride, i64 off, int sensor) {
   if (n <= 0) return 0;
   PDL(k_index_error<T>, cdiv(n, 256), 256, 0, h->dc, q, pts, n, stride, h->xyzv + off, h->pidx + off, (const float*)h->map,
-      h->sc, h->fs, h->rays + off, h->ray_ctl + 2 * sensor, (const float*)(h->steps + 1));
+      h->sc, h->fs, h->rays + off, h->ray_ctl + 2 * sensor, (const unsigned short*)h->step_cnt);
   LAUNCH_CHECK();
   return 0;
 }
@@ -431,13 +432,20 @@ RayGrid ray_grid(const emap_handle* h, int align) {
       if (ax == 0) { r0 = std::min(r0, a); r1 = std::max(r1, b); } else { c0 = std::min(c0, a); c1 = std::max(c1, b); }
     }
   }
-  RayGrid g{0, 0, 0, 0, 3};
+  RayGrid g{0, 0, 0, 0, 3, 0, 0};
   if (r1 <= r0 || c1 <= c0) return g;
   c0 = (c0 / align) * align; c1 = std::min(W, ((c1 + align - 1) / align) * align);
   g.r0 = r0; g.r1 = r1; g.c0 = c0; g.c1 = c1;
-  int ts = 2;
-  while ((RT << ts) < std::max(r1 - r0, c1 - c0) || (4 << ts) < h->span_cells + 1) ts++;
-  g.ts = ts;
+  // tiles are aligned to the map (tile = cell >> ts) and the coarse maps start at a double-tile boundary at or before
+  // (r0, c0): RT tiles per axis must reach the far edge of the box from there
+  for (int ts = 2;; ts++) {
+    const int al = 2 << ts;
+    const int r0a = (r0 / al) * al, c0a = (c0 / al) * al;
+    if ((RT << ts) >= std::max(r1 - r0a, c1 - c0a) && (4 << ts) >= h->span_cells + 1) {
+      g.ts = ts; g.ta = r0a >> ts; g.tb = c0a >> ts;
+      break;
+    }
+  }
   return g;
 }
 
@@ -599,6 +607,7 @@ int emap_create(const emap_config* cfg, int device, emap_handle** out) {
   ALLOC(h->fs, sizeof(FrameScalars));
   ALLOC(h->lut, sizeof(unsigned short) * 65536);
   ALLOC(h->tmap, sizeof(u32) * RT * RT);
+  ALLOC(h->step_cnt, sizeof(unsigned short) * (0x7c00 + 8));
   ALLOC(h->d_export, sizeof(float) * C);
   h->d_export_floats = C;
   // march table as k_raycast reads it: [0] unused (lane 0 of the first warp iteration), [1 + k] = s_k, +inf padding up to
@@ -622,13 +631,14 @@ int emap_create(const emap_config* cfg, int device, emap_handle** out) {
   TRY(cudaMemsetAsync(h->fs, 0, sizeof(FrameScalars), h->stream));
   {
     std::vector<float> tab((size_t)h->n_tab, INFINITY);
-    tab[0] = 0.f;
+    tab[0] = NAN;       // "step -1" of lane 0 in a ray's first warp iteration: NaN -> cell (0, 0), see k_raycast
     for (size_t k = 0; k < h->steps_host.size(); k++) tab[1 + k] = h->steps_host[k];
     // pageable source: the copy is staged before the call returns, and the stream is synchronised below
     TRY(cudaMemcpyAsync(h->steps, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, h->stream));
     TRY(cudaStreamSynchronize(h->stream));
   }
   k_build_lut<<<256, 256, 0, h->stream>>>(h->dc, h->lut);
+  k_build_step_cnt<<<cdiv(0x7c01, 256), 256, 0, h->stream>>>((const float*)(h->steps + 1), h->dc.n_steps, h->step_cnt);
   k_init<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map);
   h->launches += 2;
   if (post_smem(h->dc) > 48 * 1024)
@@ -682,7 +692,7 @@ int emap_destroy(emap_handle* h) {
   if (h->attached) { h->u32_block = nullptr; h->i64_block = nullptr; h->sc.last = nullptr; h->sc.rec = nullptr; h->sc.ukv = nullptr; h->fs = nullptr; }
   void* ptrs[] = {h->map, h->map_alt, h->normal, h->trav_input, h->u32_block, h->i64_block, h->sc.last, h->sc.rec,
                   h->sc.ukv, h->ukey_x, h->fs, h->steps, h->d_export, h->d_in[0], h->d_in[1], h->xyzv, h->pidx, h->pl[0], h->pl[1],
-                  h->pl[2], h->pl[3], h->pl_cnt, h->rays, h->ray_ctl, h->sc.thr, h->dirty, h->lut, h->tmap, h->ip_block, h->sem_fsum, h->sem_csum};
+                  h->pl[2], h->pl[3], h->pl_cnt, h->rays, h->ray_ctl, h->sc.thr, h->dirty, h->lut, h->step_cnt, h->tmap, h->ip_block, h->sem_fsum, h->sem_csum};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int b = 0; b < 2; b++) if (h->in_free[b]) cudaEventDestroy(h->in_free[b]);
   if (h->copy_done) cudaEventDestroy(h->copy_done);
@@ -707,8 +717,11 @@ int emap_destroy(emap_handle* h) {
 int emap_set_traversability_weights(emap_handle* h, const float* w1, const float* w2, const float* w3, const float* w_out) {
   ENTER(h);
   if (!w1 || !w2 || !w3 || !w_out) return fail(h, EMAP_ERR_INVALID, "null weights");
-  memcpy(h->dc.w1, w1, sizeof(float) * 36); memcpy(h->dc.w2, w2, sizeof(float) * 36);
-  memcpy(h->dc.w3, w3, sizeof(float) * 36); memcpy(h->dc.wout, w_out, sizeof(float) * 12);
+  const float* wl[3] = {w1, w2, w3};
+  for (int l = 0; l < 3; l++)
+    for (int cp = 0; cp < 2; cp++)
+      for (int j = 0; j < 9; j++) h->dc.wp[l][cp][j] = make_float2(wl[l][(2 * cp) * 9 + j], wl[l][(2 * cp + 1) * 9 + j]);
+  memcpy(h->dc.wout, w_out, sizeof(float) * 12);
   return EMAP_OK;
 }
 
@@ -1355,6 +1368,9 @@ int emap_inpaint(emap_handle* h, const float* elevation, const float* is_valid, 
     if (h->ip_block) cudaFree(h->ip_block);
     h->ip_block = nullptr; h->ip_bytes = 0;
     CK(cudaMalloc(&h->ip_block, need));
+    // once: the march loads a pixel's child fields (ck, Tc, vc) speculatively, before it knows the pixel is a child of the
+    // running round; the values of non-children are never used, but they should not be uninitialised memory
+    CK(cudaMemsetAsync(h->ip_block, 0, need, h->stream));
     h->ip_bytes = need;
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_ip_march, IP_MARCH_THREADS, 0));

@@ -52,7 +52,8 @@ struct DevCfg {
   float overlap_z_f, time_var_f, time_int_f;
   u32 lut_lim2;                // half2 {LIM, LIM}: the march clamps fp16 coordinates to [-LIM, LIM] before the cell look-up
   int lut_p2;                  // bytes of one half (positive / negative fp16 patterns) of the shared-memory cell table
-  float w1[36], w2[36], w3[36], wout[12];
+  float2 wp[3][2][9];          // traversability conv weights: layer, channel pair p, tap -> {w[2p][tap], w[2p+1][tap]} (FFMA2 operands)
+  float wout[12];
 };
 
 struct Pose {                  // one sensor: R and t rounded to fp16 where the reference does (CK.py:54-57,62-69,83-85)

@@ -39,10 +39,10 @@ struct CellScratch {
 };
 
 // Geometry of the cells a ray of this frame can reach, and of the coarse maps over them (ray_box in emap_api.cu):
-// rows [r0, r1) x columns [c0, c1) (c0, c1 multiples of 4 when W is); fine tiles of 2^ts x 2^ts cells, at most
-// RT x RT of them, origin (r0, c0).
+// rows [r0, r1) x columns [c0, c1) (c0, c1 multiples of 4 when W is); fine tiles of 2^ts x 2^ts cells aligned to the
+// map (tile of a cell = cell >> ts), at most RT x RT of them from tile (ta, tb) on, covering the whole box.
 #define RT 64                     // fine tiles per axis of the coarse ray maps
-struct RayGrid { int r0, r1, c0, c1, ts; };
+struct RayGrid { int r0, r1, c0, c1, ts, ta, tb; };   // (ta, tb): tile coordinates (cell >> ts) of the coarse maps' origin, both even
 
 // accumulate into the per-cell scratch: local L2 atomic, or one in-switch multicast reduction
 __device__ __forceinline__ void red_add(u32* p, u32 v, i64 mc) {
@@ -67,6 +67,10 @@ __device__ __forceinline__ void red_min(u32* p, u32 v, i64 mc) {
 // needs them (pdl_wait).  With the attribute absent both are no-ops.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+#ifndef FUSE_AGG
+#define FUSE_AGG 1                // single-GPU frames: warp-aggregate the per-cell atomics of a warp that has runs (0: never)
+#endif
 
 // ---- warp aggregation of pushes over RUNS of adjacent lanes that hit the same cell (scan-ordered
 // clouds put consecutive points in the same cell).  Every accumulation is an integer sum / max, so
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(256)
 k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64 n, const i64 stride,
               float4* __restrict__ xyzv, int* __restrict__ pidx, const float* __restrict__ map,
               const CellScratch s, FrameScalars* fs, Ray* __restrict__ rays, int* __restrict__ ray_ctl,
-              const float* __restrict__ steps) {
+              const unsigned short* __restrict__ step_cnt) {
   pdl_trigger(); pdl_wait();
   const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   i64 e = 0; int ec = 0, nv = 0;
@@ -165,8 +169,13 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
         const float m = fmaxf(fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fabsf(g.z)),
                               fmaxf(fmaxf(fabsf(q.t[0]), fabsf(q.t[1])), fabsf(q.t[2])));
         const float len_far = norm - (0.325f + 1e-3f * (2.f * m + 2.f * norm));
-        // number of march steps below len / len_far: s_k is strictly increasing (steps[k] = s_k, +inf padded)
-        ray.counts = (u32)count_below(steps, c.n_steps, ray.len) | ((u32)count_below(steps, c.n_steps, len_far) << 16);
+        // number of march steps below len / len_far, from the per-handle table over the non-negative fp16 values
+        // (k_build_step_cnt).  len is an fp16 value: exact.  len_far is rounded DOWN to fp16 first: the count can only
+        // get smaller, i.e. the `d < 0.1` test is evaluated for a few more samples than necessary -- same results.
+        const u32 n_act = __ldg(step_cnt + __half_as_ushort(__float2half_rn(ray.len)));
+        u32 k_far = 0;
+        if (len_far > 0.f) k_far = __ldg(step_cnt + min((u32)__half_as_ushort(__float2half_rd(len_far)), 0x7c00u));
+        ray.counts = n_act | (k_far << 16);
       }
       if (g.valid && g.inside) {                                  // CK.py:318-323
         const float mh = __ldg(map + idx), mv = __ldg(map + c.C + idx);
@@ -177,18 +186,23 @@ k_index_error(const DevCfg c, const Pose q, const T* __restrict__ pts, const i64
           is_inl = true;
         }
         cell_key = idx;
-        if (!s.mc_off) atomicAdd(s.cnt_ai + idx, is_inl ? 0x100000001ull : 1ull);
         if (s.dirty) s.dirty[idx] = 1;
       }
     }
     xyzv[i] = o; pidx[i] = rec;
   }
-  if (s.mc_off) {   // sharded frame: one multicast reduction per run of lanes in the same cell
+  {   // per-cell counts (CK.py:334,336).  Sharded frame: one multicast reduction per run of lanes in the same cell.
+      // Single GPU: one atomic per point, or per run when the warp has runs at all (scan-ordered clouds)
     const int lane = threadIdx.x & 31;
-    const RunInfo ri = run_of(cell_key, lane);
-    const u32 inl = __ballot_sync(0xffffffffu, is_inl) & ri.run_mask;
-    if (ri.tail && cell_key >= 0) {
-      red_add(s.cnt_ai + cell_key, (u64)__popc(ri.run_mask) | ((u64)__popc(inl) << 32), s.mc_off);
+    const int below = __shfl_up_sync(0xffffffffu, cell_key, 1);
+    const bool agg = s.mc_off || (FUSE_AGG && __any_sync(0xffffffffu, lane > 0 && cell_key >= 0 && cell_key == below));
+    if (!agg) {
+      if (cell_key >= 0) atomicAdd(s.cnt_ai + cell_key, is_inl ? 0x100000001ull : 1ull);
+    } else {
+      const RunInfo ri = run_of(cell_key, lane);
+      const u32 inl = __ballot_sync(0xffffffffu, is_inl) & ri.run_mask;
+      if (ri.tail && cell_key >= 0)
+        red_add(s.cnt_ai + cell_key, (u64)__popc(ri.run_mask) | ((u64)__popc(inl) << 32), s.mc_off);
     }
   }
   // compact the rays that have at least one march step (s_0 < len) into the sensor's ray list: one
@@ -298,16 +312,23 @@ k_fuse(const DevCfg c, const i64 n, const i64 global_off, const float4* __restri
       }
     }
   }
-  if (!s.mc_off) {                        // single GPU: plain L2 atomics
-    if ((PUSH & 1) && (is_out || is_fused)) atomicAdd(s.cnt_fo + idx, is_out ? 0x100000000ull : 1ull);
-    if ((PUSH & 2) && is_fused) {
-      atomicAdd((u64*)(s.SH + idx), (u64)fh);
-      atomicAdd((u64*)(s.SV + idx), (u64)fv);
-      atomicMax(s.last + idx, key);
+  if (!s.mc_off) {
+    // single GPU: plain L2 atomics -- unless some lane shares its cell with the lane below it (scan-ordered clouds:
+    // LiDAR rings, depth-image rows), in which case the warp takes the run-aggregated path below (one atomic per run
+    // and quantity instead of one per point; exact, every accumulation is an integer sum / max)
+    const int below = __shfl_up_sync(0xffffffffu, idx, 1);
+    const bool agg = FUSE_AGG && __any_sync(0xffffffffu, lane > 0 && idx >= 0 && idx == below);
+    if (!agg) {
+      if ((PUSH & 1) && (is_out || is_fused)) atomicAdd(s.cnt_fo + idx, is_out ? 0x100000000ull : 1ull);
+      if ((PUSH & 2) && is_fused) {
+        atomicAdd((u64*)(s.SH + idx), (u64)fh);
+        atomicAdd((u64*)(s.SV + idx), (u64)fv);
+        atomicMax(s.last + idx, key);
+      }
+      return;
     }
-    return;
   }
-  // sharded frame: pre-reduce each run of lanes in the same cell, one multicast reduction per quantity
+  // pre-reduce each run of lanes in the same cell: one atomic (sharded frame: one multicast reduction) per quantity
   const RunInfo ri = run_of(idx, lane);
   const u32 outs = __ballot_sync(0xffffffffu, is_out) & ri.run_mask;
   const u32 fus = __ballot_sync(0xffffffffu, is_fused) & ri.run_mask;
@@ -415,7 +436,7 @@ k_record(const DevCfg c, const float* __restrict__ map, const CellScratch s, con
     float m = -inf;
 #pragma unroll
     for (int j = 0; j < V; j++) m = fmaxf(m, (ot[j] != ot[j]) ? inf : ot[j]);     // NaN threshold: never cull
-    if (m > -inf) atomicMax(tmap + (((rr - g.r0) >> g.ts) * RT + ((cc0 - g.c0) >> g.ts)), fkey(m));
+    if (m > -inf) atomicMax(tmap + (((rr >> g.ts) - g.ta) * RT + ((cc0 >> g.ts) - g.tb)), fkey(m));
   }
   if (V == 4) {
     uint4* dst = reinterpret_cast<uint4*>(s.rec + i0);
@@ -424,6 +445,13 @@ k_record(const DevCfg c, const float* __restrict__ map, const CellScratch s, con
   } else {
     for (int j = 0; j < V; j++) s.rec[i0 + j] = make_uint2(oa[j], ofl[j]);
   }
+}
+
+// step_cnt[b] = number of march steps s_k < x for the non-negative fp16 value x with bit pattern b (0 .. 0x7c00 = +inf)
+__global__ void __launch_bounds__(256) k_build_step_cnt(const float* __restrict__ steps, int n_steps, unsigned short* __restrict__ step_cnt) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > 0x7c00) return;
+  step_cnt[b] = (unsigned short)count_below(steps, n_steps, __half2float(__ushort_as_half((unsigned short)b)));
 }
 
 // fill the per-handle cell table (all 65536 fp16 bit patterns, CK.py:22-33 in its exact double form)
@@ -520,6 +548,7 @@ k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __res
   const u32 s_steps_a = s_lut + (u32)lay.off_steps;               // shared-space address of s_tab[0]
   const u32 s_t8_a = s_lut + (u32)lay.off_t8, s_t16_a = s_lut + (u32)lay.off_t16;
   const int ts = g.ts;
+  const u32 s_t8_o = s_t8_a - 4u * (u32)(g.ta * RT + g.tb);      // address of the (virtual) entry of tile (0, 0)
   int n_steps_done = 0, n_visits = 0;
   // Work queue: one global counter; a warp draws RC_BATCH consecutive rays per atomic (all warps hammering ONE address
   // serialise at ~0.8 ns per atomic, which bounded the kernel at one ray per atomic) and prefetches its next batch
@@ -550,7 +579,7 @@ k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __res
         rc_cell(s_lut, lim2, nlim2, __fmaf_rn(rx, sa, tx), __fmaf_rn(ry, sa, ty), ixa, iya);
         rc_cell(s_lut, lim2, nlim2, __fmaf_rn(rx, sb, tx), __fmaf_rn(ry, sb, ty), ixb, iyb);
         const float zmin = fminf(__fmaf_rn(rz, sa, tz), __fmaf_rn(rz, sb, tz));
-        const int A = ((int)min(ixa, ixb) - g.r0) >> (ts + 1), B = ((int)min(iya, iyb) - g.c0) >> (ts + 1);
+        const int A = (int)(min(ixa, ixb) >> (ts + 1)) - (g.ta >> 1), B = (int)(min(iya, iyb) >> (ts + 1)) - (g.tb >> 1);
         if (live && !COUNT && (unsigned)A < RT / 2 && (unsigned)B < RT / 2) {
           float m;
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m) : "r"(s_t16_a + 4u * (u32)(A * (RT / 2) + B)));
@@ -563,25 +592,24 @@ k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __res
         todo &= todo - 1;
         // lane l handles step k = it*31 + l - 1 (k = -1: none); lane 0 only supplies the previous cell
         const int k = it * RC_STRIDE + lane - 1;
+        // lanes past the ray's end repeat its last step (same cell as their predecessor: skipped by CK.py:209 below); lane 0
+        // of the first iteration reads the table's NaN entry -> cell (0, 0), a border cell no ray acts on
+        const int kc = min(k, n_act - 1);
         float sk;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sk) : "r"(s_steps_a + 4u * (u32)(k + 1)));
-        const bool act = (unsigned)k < (unsigned)n_act;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sk) : "r"(s_steps_a + 4u * (u32)(kc + 1)));
         const float nx = __fmaf_rn(rx, sk, tx);                   // t + ray*s: product exact (CK.py:205-207)
         const float ny = __fmaf_rn(ry, sk, ty);
         u32 ix, iy;
         rc_cell(s_lut, lim2, nlim2, nx, ny, ix, iy);
-        const int nidx = act ? (int)(ix * (u32)W + iy) : -2;
+        const int nidx = (int)(ix * (u32)W + iy);
         const int prev = __shfl_up_sync(0xffffffffu, nidx, 1);    // lane 0 gets its own value back: never visits
-        if (COUNT) n_steps_done += act && lane != 0;
-        if (nidx == prev || !act) continue;                       // CK.py:209 (CK.py:211: border cells are skipped via thr = -inf)
+        if (COUNT) n_steps_done += ((unsigned)k < (unsigned)n_act) && lane != 0;
+        if (nidx == prev) continue;                               // CK.py:209 (CK.py:211: border cells are skipped via thr = -inf)
         const float nz = __fmaf_rn(rz, sk, tz);
-        if (!COUNT) {   // coarse level: the fine tile's maximum
-          const int a = ((int)ix - g.r0) >> ts, b = ((int)iy - g.c0) >> ts;
-          if ((unsigned)a < RT && (unsigned)b < RT) {
-            float m;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m) : "r"(s_t8_a + 4u * (u32)(a * RT + b)));
-            if (nz > m) continue;
-          }
+        if (!COUNT) {   // coarse level: the fine tile's maximum (every cell a ray of this frame reaches lies in the tiled box)
+          float m;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m) : "r"(s_t8_o + (ix >> ts) * (4u * RT) + ((iy >> ts) << 2)));
+          if (nz > m) continue;
         }
         if (COUNT) {   // statistics mode: count the cells examined past the skips of CK.py:209-226, as the oracle does
           bool near = false;
@@ -791,7 +819,20 @@ k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const F
 // One CTA per PT_Y x PT_X tile; the (tile + halo) of the two input planes is staged in shared
 // memory once, the dilated tile (+3 halo) stays in shared memory for the CNN and the normals.
 #define PT_X 32
+#ifndef PT_Y
 #define PT_Y 16
+#endif
+
+// two fp32 FMAs in one instruction (Blackwell FFMA2): acc.{x,y} = fma(w.{x,y}, t, acc.{x,y}), each IEEE round-to-nearest
+// (bit-identical to two fmaf); the scalar tap is broadcast by the instruction's operand modifier.
+__device__ __forceinline__ void ffma2(float2& acc, const float2 w, const float t) {
+  u64 a, ww, tt;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(acc.x), "f"(acc.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w.x), "f"(w.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(tt) : "f"(t));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(ww), "l"(tt));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a));
+}
 
 // K = dilation_size as a compile-time constant (0 = use c.dilation at run time).
 template <int KT>
@@ -890,20 +931,37 @@ k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, 
           // neighbour (dy,dx) at bit s' = (dx+K)+(dy+K): the reference's strict-< scan (CK.py:429-438)
           // picks the smallest dx+dy, ties to the smallest dy == lowest set bit of the OR, then the
           // first row that has it.  Branch-free, all lanes.
-          const u32 wmask = (1u << (2 * K + 1)) - 1u;
-          u32 any = 0;
+          if (KT) {
+            // compile-time K: the shifted row windows stay in registers; the winner row is the first whose term has bit s'
+            constexpr int KK = KT ? KT : 1;
+            const u32 wmask = (1u << (2 * KK + 1)) - 1u;
+            u32 term[2 * KK + 1], any = 0;
 #pragma unroll
-          for (int dy = -K; dy <= K; dy++)
-            any |= ((u32)(s_rowsel[sa + dy] >> (sb - K)) & wmask) << (dy + K);
-          if (any) {
-            const int sp = __ffs(any) - 1;                       // s' of the winner
-            int dyw = K;
-#pragma unroll
-            for (int dy = K; dy >= -K; dy--) {
-              const int dx = sp - (dy + K) - K;
-              if (dx >= -K && dx <= K && ((s_rowsel[sa + dy] >> (sb + dx)) & 1ull)) dyw = dy;
+            for (int i = 0; i <= 2 * KK; i++) {
+              term[i] = ((u32)(s_rowsel[sa + i - KK] >> (sb - KK)) & wmask) << i;
+              any |= term[i];
             }
-            out = s_up[(sa + dyw) * B + sb + (sp - (dyw + K) - K)];
+            if (any) {
+              const int sp = __ffs(any) - 1;                     // s' of the winner
+              int iw = 2 * KK;
+#pragma unroll
+              for (int i = 2 * KK - 1; i >= 0; i--) if ((term[i] >> sp) & 1u) iw = i;
+              out = s_up[(sa + iw - KK) * B + sb + (sp - iw - KK)];
+            }
+          } else {
+            const u64 wmask = (1ull << (2 * K + 1)) - 1ull;      // s' reaches 4K = 32 at K = 8: 64-bit words
+            u64 any = 0;
+            for (int dy = -K; dy <= K; dy++)
+              any |= ((s_rowsel[sa + dy] >> (sb - K)) & wmask) << (dy + K);
+            if (any) {
+              const int sp = __ffsll((long long)any) - 1;
+              int dyw = K;
+              for (int dy = K; dy >= -K; dy--) {
+                const int dx = sp - (dy + K) - K;
+                if (dx >= -K && dx <= K && ((s_rowsel[sa + dy] >> (sb + dx)) & 1ull)) dyw = dy;
+              }
+              out = s_up[(sa + dyw) * B + sb + (sp - (dyw + K) - K)];
+            }
           }
         }
       }
@@ -917,10 +975,15 @@ k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, 
   if (K >= 2 && (c0 - 3 < K - 1 || c0 + PT_X + 3 > W - K)) {       // block-uniform condition
     __syncthreads();     // the loop above stored a placeholder for these cells from OTHER threads: order the two writes
     const int lane = tid & 31, warp = tid >> 5, side = 2 * K + 1;
-    for (int e = warp; e < DA * DB; e += 8) {
-      const int a = e / DB, b = e - a * DB;
-      const int r = r0 - 3 + a, cc = c0 - 3 + b;
-      if (r < 0 || r >= W || cc < 0 || cc >= W || (cc >= K - 1 && cc <= W - K)) continue;    // warp-uniform
+    // the border columns this tile (+3 halo) covers: [la, la + nl) on the left edge, [ra, ra + nr) on the right edge
+    const int la = max(c0 - 3, 0), nl = max(0, min(c0 - 3 + DB - 1, K - 2) - la + 1);
+    const int ra = max(max(c0 - 3, W - K + 1), K - 1), nr = max(0, min(c0 - 3 + DB - 1, W - 1) - ra + 1);
+    const int nc = nl + nr;
+    for (int e2 = warp; e2 < DA * nc; e2 += 8) {
+      const int a = e2 / nc, j = e2 - a * nc;
+      const int r = r0 - 3 + a, cc = j < nl ? la + j : ra + (j - nl);
+      const int e = a * DB + (cc - (c0 - 3));
+      if (r < 0 || r >= W) continue;                                                           // warp-uniform
       const int i = r * W + cc;
       float out = up[i];
       if (__fadd_rn(valid[i], isup[i]) < 0.5f) {
@@ -960,18 +1023,18 @@ k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, 
 #pragma unroll
       for (int l = 0; l < 3; l++) {
         const int dil = l + 1;
-        const float* wl = (l == 0) ? c.w1 : (l == 1) ? c.w2 : c.w3;
         float t[9];
 #pragma unroll
         for (int p = 0; p < 3; p++)
 #pragma unroll
           for (int qq = 0; qq < 3; qq++) t[p * 3 + qq] = d[(p - 1) * dil * DB + (qq - 1) * dil];
 #pragma unroll
-        for (int ch = 0; ch < 4; ch++) {
-          float sacc = 0.f;
+        for (int cp = 0; cp < 2; cp++) {                           // channels 2cp, 2cp+1: one FFMA2 per tap
+          float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int j = 0; j < 9; j++) sacc = __fmaf_rn(wl[ch * 9 + j], t[j], sacc);
-          acc = __fmaf_rn(c.wout[l * 4 + ch], fabsf(sacc), acc);
+          for (int j = 0; j < 9; j++) ffma2(s2, c.wp[l][cp][j], t[j]);
+          acc = __fmaf_rn(c.wout[l * 4 + 2 * cp], fabsf(s2.x), acc);
+          acc = __fmaf_rn(c.wout[l * 4 + 2 * cp + 1], fabsf(s2.y), acc);
         }
       }
       map[3 * C + gi] = expf(-acc);
