@@ -38,6 +38,8 @@ struct emap_handle {
   // state
   float* map = nullptr;       // (7,W,W)
   float* map_alt = nullptr;   // shift target
+  CUtensorMap post_tm[2];     // TMA descriptors of the two state buffers as (W, W, 7) fp32 tensors, box = k_post's staged tile
+  const float* post_tm_base[2] = {nullptr, nullptr};
   float* normal = nullptr;    // (3,W,W)
   float* trav_input = nullptr;
   float center[3] = {0, 0, 0};        // fp32 like EM.py:61
@@ -66,7 +68,7 @@ struct emap_handle {
   float4* xyzv = nullptr;
   int* pidx = nullptr;
   Ray* rays = nullptr;        // compacted rays of the frame, one segment per sensor (at the sensor's point offset)
-  int* ray_ctl = nullptr;     // per sensor: {ray count, work counter}; zero between frames (k_finalize)
+  int* ray_ctl = nullptr;     // per sensor: RC_CTL ints {ray count, work-queue counters}; zero between frames (k_finalize)
   int ray_ctl_cap = 0;        // sensors
   bool overlap_override = false;
   float overlap_z_override = 0.f;
@@ -78,6 +80,7 @@ struct emap_handle {
   i64 n_points = 0, global_off = 0;
   float pos_noise = 0, ori_noise = 0;
   int phase = 0;              // sharded-frame state machine
+  bool fused_drift = false;   // single-GPU frame: no k_drift launch (k_fuse decides, k_finalize resets)
   // multicast-attached scratch (sharded frames over NVLink multicast, emap_shard_attach)
   bool attached = false;
   std::vector<const void*> pend_pts;   // device pointers of the frame's clouds (index pass deferred to phase 0)
@@ -259,7 +262,7 @@ template <typename T>
 int launch_index(emap_handle* h, const Pose& q, const T* pts, i64 n, i64 stride, i64 off, int sensor) {
   if (n <= 0) return 0;
   PDL(k_index_error<T>, cdiv(n, 256), 256, 0, h->dc, q, pts, n, stride, h->xyzv + off, h->pidx + off, (const float*)h->map,
-      h->sc, h->fs, h->rays + off, h->ray_ctl + 2 * sensor, (const unsigned short*)h->step_cnt);
+      h->sc, h->fs, h->rays + off, h->ray_ctl + RC_CTL * sensor, (const unsigned short*)h->step_cnt);
   LAUNCH_CHECK();
   return 0;
 }
@@ -269,6 +272,7 @@ int frame_begin(emap_handle* h, int32_t n_sensors, const void* const* points, co
                 int dtype, int is_device_ptr, const float* R, const float* t, int64_t global_off, float pn, float on,
                 bool sharded) {
   h->sc.dirty = sharded ? nullptr : h->dirty;      // sharded frames derive the marker from the all-reduced counts
+  h->fused_drift = !sharded;
   if (n_sensors < 1 || row_stride < 3 || (dtype != EMAP_F32 && dtype != EMAP_F64))
     return fail(h, EMAP_ERR_INVALID, "emap_input: n_sensors >= 1, row_stride >= 3, dtype f32/f64 required");
   const size_t esz = dtype == EMAP_F32 ? 4 : 8;
@@ -293,8 +297,8 @@ int frame_begin(emap_handle* h, int32_t n_sensors, const void* const* points, co
     CK(cudaStreamSynchronize(h->stream));
     if (h->ray_ctl) cudaFree(h->ray_ctl);
     h->ray_ctl = nullptr; h->ray_ctl_cap = 0;
-    CK(cudaMalloc(&h->ray_ctl, sizeof(int) * 2 * (n_sensors + 8)));
-    CK(cudaMemsetAsync(h->ray_ctl, 0, sizeof(int) * 2 * (n_sensors + 8), h->stream));   // ordered before the frame's kernels
+    CK(cudaMalloc(&h->ray_ctl, sizeof(int) * RC_CTL * (n_sensors + 8)));
+    CK(cudaMemsetAsync(h->ray_ctl, 0, sizeof(int) * RC_CTL * (n_sensors + 8), h->stream));   // ordered before the frame's kernels
     h->ray_ctl_cap = n_sensors + 8;
   }
   h->overlap_override = false;
@@ -364,19 +368,26 @@ int frame_index(emap_handle* h) {
 
 int frame_fuse(emap_handle* h) {
   NvtxRange nv("emap:drift+fusion");
-  PDL(k_drift, 1, 256, 0, h->dc, h->fs, h->pos_noise, h->ori_noise,
-      h->overlap_override ? h->overlap_z_override : h->poses[0].t[2], 1, h->tmap);
-  LAUNCH_CHECK();
+  const float overlap_tz = h->overlap_override ? h->overlap_z_override : h->poses[0].t[2];
+  if (!h->fused_drift) {
+    PDL(k_drift, 1, 256, 0, h->dc, h->fs, h->pos_noise, h->ori_noise, overlap_tz, 1, h->tmap);
+    LAUNCH_CHECK();
+  }
   if (stage_mark(h, 2)) return EMAP_ERR_CUDA;
-  if (h->n_points > 0) {
+  if (h->fused_drift) {
+    // single GPU: the drift decision is derived inside k_fuse (launched even for an empty frame: it publishes the statistics)
+    PDL((k_fuse<3, 1>), std::max(1, cdiv(h->n_points, 256)), 256, 0, h->dc, h->n_points, h->global_off, (const float4*)h->xyzv,
+        (const int*)h->pidx, (const float*)h->map, h->sc, (const FrameScalars*)h->fs, h->fs, h->pos_noise, h->ori_noise, overlap_tz);
+    LAUNCH_CHECK();
+  } else if (h->n_points > 0) {
     if (h->attached) {
       // NVLink multicast: only the counts are on the critical path; sums + last-writer keys follow on the side stream
       // (frame_rays), under the ray-cast
-      PDL(k_fuse<1>, cdiv(h->n_points, 256), 256, 0, h->dc, h->n_points, h->global_off, (const float4*)h->xyzv,
-          (const int*)h->pidx, (const float*)h->map, h->sc, (const FrameScalars*)h->fs);
+      PDL((k_fuse<1, 0>), cdiv(h->n_points, 256), 256, 0, h->dc, h->n_points, h->global_off, (const float4*)h->xyzv,
+          (const int*)h->pidx, (const float*)h->map, h->sc, (const FrameScalars*)h->fs, h->fs, 0.f, 0.f, 0.f);
     } else {
-      PDL(k_fuse<3>, cdiv(h->n_points, 256), 256, 0, h->dc, h->n_points, h->global_off, (const float4*)h->xyzv,
-          (const int*)h->pidx, (const float*)h->map, h->sc, (const FrameScalars*)h->fs);
+      PDL((k_fuse<3, 0>), cdiv(h->n_points, 256), 256, 0, h->dc, h->n_points, h->global_off, (const float4*)h->xyzv,
+          (const int*)h->pidx, (const float*)h->map, h->sc, (const FrameScalars*)h->fs, h->fs, 0.f, 0.f, 0.f);
     }
     LAUNCH_CHECK();
   }
@@ -455,9 +466,9 @@ int frame_rays(emap_handle* h) {
   if (deferred) {   // sums + last-writer keys of the fusion: multicast pushes on the side stream, under the ray-cast
     CK(cudaEventRecord(h->ev_fork, h->stream));
     CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-    k_fuse<2><<<cdiv(h->n_points, 256), 256, 0, h->side_stream>>>(h->dc, h->n_points, h->global_off, (const float4*)h->xyzv,
-                                                                    (const int*)h->pidx, (const float*)h->map, h->sc,
-                                                                    (const FrameScalars*)h->fs);
+    k_fuse<2, 0><<<cdiv(h->n_points, 256), 256, 0, h->side_stream>>>(h->dc, h->n_points, h->global_off, (const float4*)h->xyzv,
+                                                                       (const int*)h->pidx, (const float*)h->map, h->sc,
+                                                                       (const FrameScalars*)h->fs, h->fs, 0.f, 0.f, 0.f);
     LAUNCH_CHECK();
     CK(cudaEventRecord(h->ev_join, h->side_stream));
   }
@@ -477,10 +488,10 @@ int frame_rays(emap_handle* h) {
       // persistent grid: enough CTAs to fill every SM, never more than one warp per possible ray
       const int grid = (int)std::min<i64>((i64)h->n_sm * h->rc_blocks_per_sm, (n + RC_THREADS / 32 - 1) / (RC_THREADS / 32));
       if (h->count_rays)
-        PDL(k_raycast<true>, grid, RC_THREADS, h->rc_smem, h->dc, h->poses[s], (const Ray*)(h->rays + h->offs[s]), h->ray_ctl + 2 * (int)s,
+        PDL(k_raycast<true>, grid, RC_THREADS, h->rc_smem, h->dc, h->poses[s], (const Ray*)(h->rays + h->offs[s]), h->ray_ctl + RC_CTL * (int)s,
             (const float*)h->map, (const float*)h->normal, h->sc, (const float*)h->steps, h->n_tab, (const unsigned short*)h->lut, box, (const u32*)h->tmap, h->rc_lay, h->fs);
       else
-        PDL(k_raycast<false>, grid, RC_THREADS, h->rc_smem, h->dc, h->poses[s], (const Ray*)(h->rays + h->offs[s]), h->ray_ctl + 2 * (int)s,
+        PDL(k_raycast<false>, grid, RC_THREADS, h->rc_smem, h->dc, h->poses[s], (const Ray*)(h->rays + h->offs[s]), h->ray_ctl + RC_CTL * (int)s,
             (const float*)h->map, (const float*)h->normal, h->sc, (const float*)h->steps, h->n_tab, (const unsigned short*)h->lut, box, (const u32*)h->tmap, h->rc_lay, h->fs);
       LAUNCH_CHECK();
     }
@@ -493,18 +504,50 @@ int frame_rays(emap_handle* h) {
 
 size_t post_smem(const DevCfg& d) {
   const int HL = d.dilation + 3, HLX = (HL + 3) & ~3;
-  return sizeof(float) * (size_t)(3 * (PT_Y + 2 * HL) * (PT_X + 2 * HLX) + (PT_Y + 6) * (PT_X + 6) + 2)
-         + sizeof(unsigned long long) * (size_t)(PT_Y + 2 * HL + 2);
+  const size_t plane = (size_t)(((PT_Y + 2 * HL) * (PT_X + 2 * HLX) + 31) & ~31);
+  return sizeof(float) * (3 * plane + (size_t)(PT_Y + 6) * (PT_X + 6) + 2) + sizeof(unsigned long long) * (size_t)(PT_Y + 2 * HL + 2);
+}
+
+// TMA descriptor of one state buffer for k_post: tensor (x = column, y = row, z = layer), box = staged tile + halo of one
+// layer; out-of-range elements are filled with zeros.  cuTensorMapEncodeTiled is fetched from the driver at run time
+// (no link-time dependency on libcuda).
+int make_post_tm(emap_handle* h, int which, const float* base) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn)
+      return fail(h, EMAP_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    enc = (encode_fn)fn;
+  }
+  memset(&h->post_tm[which], 0, sizeof(CUtensorMap));
+  h->post_tm_base[which] = base;
+  const int W = h->dc.W;
+  if (W % 4 != 0) return 0;                                  // k_post stages with plain loads
+  const int HL = h->dc.dilation + 3, HLX = (HL + 3) & ~3;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)W, 7};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * W * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)(PT_X + 2 * HLX), (cuuint32_t)(PT_Y + 2 * HL), 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  const CUresult r = enc(&h->post_tm[which], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, EMAP_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return 0;
 }
 
 int launch_post(emap_handle* h) {
   dim3 grid(cdiv(h->dc.W, PT_X), cdiv(h->dc.W, PT_Y));
   const size_t sm = post_smem(h->dc);
+  const CUtensorMap& tm = h->post_tm[h->post_tm_base[1] == h->map ? 1 : 0];
   switch (h->dc.dilation) {
-    case 1: PDL(k_post<1>, grid, 256, sm, h->dc, h->map, h->trav_input, h->normal); break;
-    case 2: PDL(k_post<2>, grid, 256, sm, h->dc, h->map, h->trav_input, h->normal); break;
-    case 3: PDL(k_post<3>, grid, 256, sm, h->dc, h->map, h->trav_input, h->normal); break;
-    default: PDL(k_post<0>, grid, 256, sm, h->dc, h->map, h->trav_input, h->normal); break;
+    case 1: PDL(k_post<1>, grid, 256, sm, h->dc, h->map, h->trav_input, h->normal, tm); break;
+    case 2: PDL(k_post<2>, grid, 256, sm, h->dc, h->map, h->trav_input, h->normal, tm); break;
+    case 3: PDL(k_post<3>, grid, 256, sm, h->dc, h->map, h->trav_input, h->normal, tm); break;
+    default: PDL(k_post<0>, grid, 256, sm, h->dc, h->map, h->trav_input, h->normal, tm); break;
   }
   LAUNCH_CHECK();
   return 0;
@@ -512,8 +555,8 @@ int launch_post(emap_handle* h) {
 
 int frame_finish(emap_handle* h) {
   NvtxRange nv("emap:finalize+post");
-  if (h->dc.W % 4 == 0) PDL(k_finalize<4>, cdiv(h->dc.C / 4, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility, h->ray_ctl, 2 * h->ray_ctl_cap);
-  else PDL(k_finalize<1>, cdiv(h->dc.C, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility, h->ray_ctl, 2 * h->ray_ctl_cap);
+  if (h->dc.W % 4 == 0) PDL(k_finalize<4>, cdiv(h->dc.C / 4, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility, h->ray_ctl, RC_CTL * h->ray_ctl_cap, h->fused_drift ? h->fs : nullptr, h->tmap);
+  else PDL(k_finalize<1>, cdiv(h->dc.C, 256), 256, 0, h->dc, h->map, h->sc, (const FrameScalars*)h->fs, h->dc.visibility, h->ray_ctl, RC_CTL * h->ray_ctl_cap, h->fused_drift ? h->fs : nullptr, h->tmap);
   LAUNCH_CHECK();
   if (stage_mark(h, 6)) return EMAP_ERR_CUDA;
   int rc = launch_post(h);
@@ -641,6 +684,9 @@ int emap_create(const emap_config* cfg, int device, emap_handle** out) {
   k_build_step_cnt<<<cdiv(0x7c01, 256), 256, 0, h->stream>>>((const float*)(h->steps + 1), h->dc.n_steps, h->step_cnt);
   k_init<<<cdiv(h->dc.C, 256), 256, 0, h->stream>>>(h->dc, h->map);
   h->launches += 2;
+  if (make_post_tm(h, 0, h->map) || make_post_tm(h, 1, h->map_alt)) {
+    g_create_error = h->err; emap_destroy(h); return EMAP_ERR_CUDA;
+  }
   if (post_smem(h->dc) > 48 * 1024)
     TRY(cudaFuncSetAttribute(k_post<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem(h->dc)));
   {

@@ -14,6 +14,7 @@
 // makes every result independent of thread order, run-to-run deterministic and bit-identical to
 // oracle/emap_oracle.c; they are within one fp32 rounding of some order of the reference atomics.
 #pragma once
+#include <cuda.h>                 // CUtensorMap (type only; the encoder is fetched at run time, emap_api.cu)
 #include "emap_device.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -245,45 +246,71 @@ __global__ void k_set_overlap(FrameScalars* fs, float overlap_tz) {
   if (threadIdx.x == 0 && blockIdx.x == 0) fs->overlap_tz = overlap_tz;
 }
 
-// EM.py:346-357
-// Also the frame's housekeeping, so that no separate reset launch is needed: the drift accumulators are
-// consumed here and zeroed for the NEXT frame, the ray-march counters of the previous frame are cleared, the
-// overlap-clear reference is set, and the coarse ray map is reset.  (The ray work counters are re-zeroed by
-// k_finalize, after the ray-cast: every frame is the same launch sequence -> capturable as one CUDA graph.)
+// EM.py:346-357: the drift decision of a frame from the accumulated inlier statistics
+struct DriftDecision { int applied, evaluated; float shift, mean, error_sum; };
+__device__ __forceinline__ DriftDecision drift_decide(const DevCfg& c, const i64 E, const i64 ecnt, const float position_noise,
+                                                      const float orientation_noise) {
+  DriftDecision d;
+  d.applied = 0; d.evaluated = 0; d.shift = 0.f; d.mean = 0.f;
+  d.error_sum = (float)unfix32(E);
+  if (c.drift_en && (double)(float)ecnt > c.min_drift_cnt
+      && ((double)position_noise > c.pos_thresh || (double)orientation_noise > c.ori_thresh)) {
+    d.mean = __fdiv_rn(d.error_sum, (float)ecnt);
+    d.evaluated = 1;
+    if (fabsf(d.mean) < c.max_drift_f) { d.shift = __fmul_rn(d.mean, c.drift_alpha_f); d.applied = 1; }
+  }
+  return d;
+}
+// one thread: publish the decision and the frame statistics (emap_get_frame_stats), reset the ray-march counters
+__device__ __forceinline__ void drift_publish(FrameScalars* fs, const DriftDecision& d, const i64 ecnt, const float overlap_tz,
+                                              const int set_overlap) {
+  fs->nvalid_last = fs->nvalid;
+  fs->ray_steps = 0; fs->ray_visits = 0;
+  fs->ecnt_last = ecnt;
+  if (set_overlap) fs->overlap_tz = overlap_tz;
+  fs->error_sum = d.error_sum; fs->shift = d.shift; fs->applied = d.applied; fs->evaluated = d.evaluated;
+  if (d.evaluated) { fs->mean_error = d.mean; fs->additive_mean_error = __fadd_rn(fs->additive_mean_error, d.mean); }
+}
+
+// Sharded frames (the statistics arrive from all ranks between the index pass and the fusion): one thread decides.
+// Also the frame's housekeeping: the drift accumulators are consumed here and zeroed for the NEXT frame, and the coarse
+// ray map is reset.  (Single-GPU frames have no k_drift launch: every k_fuse thread derives the decision itself, see there.)
 __global__ void k_drift(const DevCfg c, FrameScalars* fs, float position_noise, float orientation_noise,
                         float overlap_tz, int set_overlap, u32* __restrict__ tmap) {
   pdl_trigger(); pdl_wait();
   for (int k = threadIdx.x; k < RT * RT; k += blockDim.x) tmap[k] = 0u;       // below every key: fkey(-inf) = 0x007fffff
   if (threadIdx.x || blockIdx.x) return;
   const i64 ecnt = fs->ecnt;
-  const float error_sum = (float)unfix32(fs->E);
-  fs->E = 0; fs->ecnt = 0;
-  fs->nvalid_last = fs->nvalid; fs->nvalid = 0;
-  fs->ray_steps = 0; fs->ray_visits = 0;
-  fs->ecnt_last = ecnt;
-  if (set_overlap) fs->overlap_tz = overlap_tz;
-  fs->error_sum = error_sum; fs->shift = 0.f; fs->applied = 0; fs->evaluated = 0;
-  if (c.drift_en && (double)(float)ecnt > c.min_drift_cnt
-      && ((double)position_noise > c.pos_thresh || (double)orientation_noise > c.ori_thresh)) {
-    const float mean = __fdiv_rn(error_sum, (float)ecnt);
-    fs->mean_error = mean; fs->evaluated = 1;
-    fs->additive_mean_error = __fadd_rn(fs->additive_mean_error, mean);
-    if (fabsf(mean) < c.max_drift_f) { fs->shift = __fmul_rn(mean, c.drift_alpha_f); fs->applied = 1; }
-  }
+  const DriftDecision d = drift_decide(c, fs->E, ecnt, position_noise, orientation_noise);
+  drift_publish(fs, d, ecnt, overlap_tz, set_overlap);
+  fs->E = 0; fs->ecnt = 0; fs->nvalid = 0;
 }
 
 // CK.py:168-197 fusion half; every load is of the pre-frame snapshot (+ drift shift)
 // PUSH: bit 0 = the counts (cnt_fo: needed by the ray-cast), bit 1 = the sums and last-writer keys (needed only by
 // k_finalize).  Single GPU: 3.  Sharded frames over NVLink multicast launch it twice: <1> on the critical path and <2>
 // on a side stream under the ray-cast, so that three of the four multicast reductions per run leave the critical path.
-template <int PUSH>
+// DRIFT = 1 (single-GPU frames): there is no k_drift launch.  The inlier statistics are complete when this kernel starts, so
+// every thread derives the drift decision itself (two broadcast loads, a handful of flops) and thread 0 publishes it for
+// the later kernels; the accumulators are re-zeroed by k_finalize, after the last reader.
+template <int PUSH, int DRIFT>
 __global__ void __launch_bounds__(256)
 k_fuse(const DevCfg c, const i64 n, const i64 global_off, const float4* __restrict__ xyzv,
        const int* __restrict__ pidx, const float* __restrict__ map, const CellScratch s,
-       const FrameScalars* __restrict__ fs) {
+       const FrameScalars* fs, FrameScalars* fsw, const float position_noise, const float orientation_noise,
+       const float overlap_tz) {
   pdl_trigger(); pdl_wait();
   const i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  int applied; float shift;
+  if (DRIFT) {
+    const i64 ecnt = fs->ecnt;
+    const DriftDecision d = drift_decide(c, fs->E, ecnt, position_noise, orientation_noise);
+    applied = d.applied; shift = d.shift;
+    if (blockIdx.x == 0 && threadIdx.x == 0) drift_publish(fsw, d, ecnt, overlap_tz, 1);
+  } else {
+    applied = fs->applied; shift = fs->shift;
+  }
   int idx = -1 - lane;                    // unique negative key: this lane pushes nothing
   bool is_out = false, is_fused = false;
   i64 fh = 0, fv = 0;
@@ -295,7 +322,7 @@ k_fuse(const DevCfg c, const i64 n, const i64 global_off, const float4* __restri
       const float4 g = xyzv[i];
       const float z = g.z, v = g.w;
       float mh = __ldg(map + idx);
-      if (fs->applied) mh = __fadd_rn(mh, fs->shift);             // EM.py:357 applied lazily
+      if (applied) mh = __fadd_rn(mh, shift);                     // EM.py:357 applied lazily
       const float mv = __ldg(map + c.C + idx);
       const float num_points = (float)(u32)s.cnt_ai[idx];         // CK.py:172
       if ((double)fabsf(mh - z) > (double)mv * c.mahal) {
@@ -476,7 +503,10 @@ __global__ void __launch_bounds__(256) k_build_lut(const DevCfg c, unsigned shor
 //     nor ray order matters.
 #define RC_THREADS 768
 #define RC_STRIDE 31              // new march steps per warp iteration
+#define RC_CTL 64                 // ints of control state per sensor: [0] ray count, [32] the work counter (128 B apart)
+#ifndef RC_BATCH
 #define RC_BATCH 4                // rays a warp draws from the work counter at a time
+#endif
 struct RcLayout { int off_t8, off_t16, off_steps, off_bar; };     // byte offsets of the shared-memory regions (host: rc_layout)
 
 // cell of the sample t + ray*s (CK.py:205-207 -> 26-33) through the staged table; all lanes must pass in-range addresses
@@ -541,7 +571,6 @@ k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __res
                    : "=r"(ok) : "r"(sbar), "r"(0) : "memory");
   }
   const int n_rays = ray_ctl[0];
-  int* next = ray_ctl + 1;
   const int W = c.W, C = c.C;
   const float tx = q.t[0], ty = q.t[1], tz = q.t[2];
   const u32 lim2 = c.lut_lim2, nlim2 = c.lut_lim2 ^ 0x80008000u;
@@ -553,6 +582,9 @@ k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __res
   // Work queue: one global counter; a warp draws RC_BATCH consecutive rays per atomic (all warps hammering ONE address
   // serialise at ~0.8 ns per atomic, which bounded the kernel at one ray per atomic) and prefetches its next batch
   // while it marches the current one.
+  // (Measured and dropped: several queues with rays dealt round-robin -- 4 % to 20 % slower, consecutive rays share cells
+  // and belong in one warp; batches of 8 -- 11 % slower at config B, the tail gets ragged.)
+  int* next = ray_ctl + 32;
   int pend = 0;
   if (lane == 0) pend = atomicAdd(next, RC_BATCH);
   int rbase = __shfl_sync(0xffffffffu, pend, 0);
@@ -739,10 +771,14 @@ __device__ __forceinline__ void finalize_cell(const DevCfg& c, float* __restrict
 template <int V>
 __global__ void __launch_bounds__(256, 4)
 k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const FrameScalars* __restrict__ fs,
-           const int rays_ran, int* __restrict__ ray_ctl, const int n_ctl) {
+           const int rays_ran, int* __restrict__ ray_ctl, const int n_ctl, FrameScalars* fs_reset, u32* __restrict__ tmap) {
   __shared__ int s_list[8][32 * V];
   pdl_trigger(); pdl_wait();
   if (blockIdx.x == 0) for (int k = threadIdx.x; k < n_ctl; k += blockDim.x) ray_ctl[k] = 0;   // consumed by k_raycast: next frame's
+  if (fs_reset && blockIdx.x == 1 % gridDim.x) {     // frames without k_drift: the housekeeping it would do for the next frame
+    for (int k = threadIdx.x; k < RT * RT; k += blockDim.x) tmap[k] = 0u;
+    if (threadIdx.x == 0) { fs_reset->E = 0; fs_reset->ecnt = 0; fs_reset->nvalid = 0; }
+  }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * V;
   const size_t C = (size_t)c.C;
@@ -837,7 +873,8 @@ __device__ __forceinline__ void ffma2(float2& acc, const float2 w, const float t
 // K = dilation_size as a compile-time constant (0 = use c.dilation at run time).
 template <int KT>
 __global__ void __launch_bounds__(256)
-k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, float* __restrict__ normal) {
+k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, float* __restrict__ normal,
+       const __grid_constant__ CUtensorMap tm) {
   extern __shared__ __align__(128) float smem[];
   pdl_trigger(); pdl_wait();
   const int W = c.W, C = c.C;
@@ -847,44 +884,38 @@ k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, 
                                                  // starts on a 16-byte boundary, as the TMA bulk copy needs
   const int A = PT_Y + 2 * HL, B = PT_X + 2 * HLX;
   constexpr int DA = PT_Y + 6, DB = PT_X + 6;
+  const int PS = (A * B + 31) & ~31;             // plane stride in floats: every staged plane starts on a 128-byte boundary (TMA)
   float* s_up = smem;                            // A*B   upper_bound
-  float* s_mask = s_up + A * B;                  // A*B   is_valid, then the raw mask = is_valid + is_upper_bound (CK.py:424)
-  float* s_iu = s_mask + A * B;                  // A*B   is_upper_bound (bulk path only)
-  float* s_dil = s_iu + A * B;                   // DA*DB dilated tile (+3 halo)
+  float* s_mask = s_up + PS;                     // A*B   is_valid, then the raw mask = is_valid + is_upper_bound (CK.py:424)
+  float* s_iu = s_mask + PS;                     // A*B   is_upper_bound (TMA path only)
+  float* s_dil = s_iu + PS;                      // DA*DB dilated tile (+3 halo)
   unsigned long long* s_rowsel = reinterpret_cast<unsigned long long*>(s_dil + DA * DB + ((DA * DB) & 1));   // A words
-  unsigned long long* s_bar = s_rowsel + A;      // mbarrier of the bulk copies
+  unsigned long long* s_bar = s_rowsel + A;      // mbarrier of the tensor copies
   const float* up = map + 5 * C; const float* valid = map + 2 * C; const float* isup = map + 6 * C;
   const int r0 = blockIdx.y * PT_Y, c0 = blockIdx.x * PT_X;
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  // Stage upper_bound / is_valid / is_upper_bound for the tile + halo.  Interior tiles: one TMA bulk copy
-  // (cp.async.bulk, 16-byte aligned row segments of B floats) per plane and row, all completing on one mbarrier;
-  // tiles touching the left / right map edge, or maps whose row pitch is not a multiple of 16 bytes: plain loads.
-  const bool bulk = (W % 4 == 0) && c0 >= HLX && c0 + PT_X + HLX <= W;
+  // Stage upper_bound / is_valid / is_upper_bound for the tile + halo: three TMA tensor copies (cp.async.bulk.tensor.3d
+  // of a B x A x 1 box of the (W, W, 7) state tensor; elements outside the map arrive as zeros) completing on one
+  // mbarrier.  Maps whose row pitch is not a multiple of 16 bytes cannot be described to the TMA unit: plain loads.
+  const bool bulk = (W % 4 == 0);
   if (bulk) {
     const u32 sbar = (u32)__cvta_generic_to_shared(s_bar);
-    const int ra = max(0, HL - r0), rb = min(A, W - r0 + HL);          // staged rows that exist in the map: [ra, rb)
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbar));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbar), "r"((rb - ra) * 3 * B * 4) : "memory");
-    }
-    __syncthreads();
-    for (int e = tid; e < 3 * A; e += 256) {
-      const int pl = e / A, a = e - pl * A;
-      float* dstp = (pl == 0 ? s_up : pl == 1 ? s_mask : s_iu) + a * B;
-      if (a >= ra && a < rb) {
-        const float* src = (pl == 0 ? up : pl == 1 ? valid : isup) + (size_t)(r0 - HL + a) * W + (c0 - HLX);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"((u32)__cvta_generic_to_shared(dstp)), "l"(src), "r"(B * 4), "r"(sbar) : "memory");
-      } else {
-        for (int b = 0; b < B; b++) dstp[b] = 0.f;                       // row outside the map
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbar), "r"(3 * A * B * 4) : "memory");
+#pragma unroll
+      for (int pl = 0; pl < 3; pl++) {
+        const u32 dst = (u32)__cvta_generic_to_shared(pl == 0 ? s_up : pl == 1 ? s_mask : s_iu);
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(dst), "l"(&tm), "r"(c0 - HLX), "r"(r0 - HL), "r"(pl == 0 ? 5 : pl == 1 ? 2 : 6), "r"(sbar) : "memory");
       }
     }
+    __syncthreads();                             // the barrier is initialised before anyone polls it
     u32 ok = 0;
     while (!ok)
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                    : "=r"(ok) : "r"(sbar), "r"(0) : "memory");
-    __syncthreads();
   }
   // raw mask + per staged row one 64-bit word whose bit b says "cell (a,b) may be SELECTED as a neighbour"
   // (CK.py:432-434: is_inside && mask > 0.5), built with warp ballots (B <= 64)
