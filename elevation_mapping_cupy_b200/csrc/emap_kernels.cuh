@@ -713,22 +713,27 @@ __device__ __forceinline__ void finalize_cell(const DevCfg& c, float* __restrict
                                               const int rr, const int cc, const int applied, const float shift,
                                               const float hmin, const float hmax, const int rays_ran) {
   const size_t C = (size_t)c.C;
+  // every load up front, also the ones only some cells need (last / sums: cells hit by points; DV: cells acted on by rays):
+  // the kernel is bound by dependent round trips to L2 / DRAM, not by bytes, so one wave of 14 loads beats two dependent ones
   const u64 fo = s.cnt_fo[i], ca = s.cnt_ai[i];
-  const u32 cf = (u32)fo, no = (u32)(fo >> 32);
   u32 nr = 0, kv = UKEY_NONE;
-  if (rays_ran) { nr = s.n_ray[i]; kv = s.ukv[i]; }
+  i64 dv_fix = 0;
+  if (rays_ran) { nr = s.n_ray[i]; kv = s.ukv[i]; dv_fix = s.DV[i]; }
+  const u64 last_key = s.last[i];
+  const i64 sh_fix = s.SH[i], sv_fix = s.SV[i];
+  const u32 cf = (u32)fo, no = (u32)(fo >> 32);
   const float h0 = map[i], v0 = map[C + i], va0 = map[2 * C + i], ti0 = map[4 * C + i], up0 = map[5 * C + i], iu0 = map[6 * C + i];
   float h = h0, v = v0, valid = va0, time = ti0, upper = up0, isup = iu0;
   if (applied) h = __fadd_rn(h, shift);                           // EM.py:357 applied lazily
   v = add_n_times(v, c.c_out, no);                                // CK.py:174
   if (cf > 0) {                                                   // CK.py:187-192
     valid = 1.f; time = 0.f; isup = 0.f;
-    upper = __uint_as_float((u32)(s.last[i] & 0xffffffffull));
+    upper = __uint_as_float((u32)(last_key & 0xffffffffull));
   }
   if (rays_ran) {
     const u32 key0 = (isup < 0.5f) ? UKEY_NONE : fkey(upper);
     if (nr > 0) {
-      valid = __fadd_rn(valid, (float)unfix32(s.DV[i]));          // CK.py:250
+      valid = __fadd_rn(valid, (float)unfix32(dv_fix));           // CK.py:250
       v = add_n_times(v, c.c_out, nr);                            // CK.py:251
     }
     // true min over rays (CK.py:230-233,253-256) of the keys carved into the cell
@@ -739,9 +744,9 @@ __device__ __forceinline__ void finalize_cell(const DevCfg& c, float* __restrict
   const float valid_in = valid;
   if (cf > 0) {
     const double cnt = (double)cf;
-    const float mean_v = (float)(unfix32(s.SV[i]) / cnt);
+    const float mean_v = (float)(unfix32(sv_fix) / cnt);
     if ((double)mean_v > c.max_variance) { h = 0.f; v = c.init_var; valid = 0.f; }
-    else { h = (float)(unfix32(s.SH[i]) / cnt); v = mean_v; valid = 1.f; }
+    else { h = (float)(unfix32(sh_fix) / cnt); v = mean_v; valid = 1.f; }
   }
   if (valid_in < 0.5f) { h = 0.f; v = c.init_var; valid = 0.f; }
   // clear_overlap_map EM.py:393-410
@@ -768,8 +773,11 @@ __device__ __forceinline__ void finalize_cell(const DevCfg& c, float* __restrict
 // selects the full path; everywhere else only the drift shift (EM.py:357) and the reset of invalid cells
 // (CK.py:380-384) remain: 3 planes read, at most 3 written, as vectors.  The cells that need the full path are
 // compacted per warp (shared-memory list) and then finalised one per LANE, so the rare path runs converged.
+#ifndef FIN_MINB
+#define FIN_MINB 4
+#endif
 template <int V>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, FIN_MINB)
 k_finalize(const DevCfg c, float* __restrict__ map, const CellScratch s, const FrameScalars* __restrict__ fs,
            const int rays_ran, int* __restrict__ ray_ctl, const int n_ctl, FrameScalars* fs_reset, u32* __restrict__ tmap) {
   __shared__ int s_list[8][32 * V];
