@@ -583,7 +583,9 @@ k_raycast(const DevCfg c, const Pose q, const Ray* __restrict__ rays, int* __res
   // serialise at ~0.8 ns per atomic, which bounded the kernel at one ray per atomic) and prefetches its next batch
   // while it marches the current one.
   // (Measured and dropped: several queues with rays dealt round-robin -- 4 % to 20 % slower, consecutive rays share cells
-  // and belong in one warp; batches of 8 -- 11 % slower at config B, the tail gets ragged.)
+  // and belong in one warp; batches of 8 -- 11 % slower at config B, the tail gets ragged; a two-level queue, CTA chunks
+  // from the global counter + shared-memory atomics per warp -- 2 % slower at B, 15 % at D: the prefetched global atomic
+  // below hides its latency under the march, a shared-memory draw at the start of every batch does not.)
   int* next = ray_ctl + 32;
   int pend = 0;
   if (lane == 0) pend = atomicAdd(next, RC_BATCH);
