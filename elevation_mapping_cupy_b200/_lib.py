@@ -52,6 +52,8 @@ SIGNATURES = {
     "emap_point_record_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "emap_get_frame_stats": (C.c_int, [C.c_void_p, C.POINTER(EmapFrameStats)]),
     "emap_set_ray_counting": (C.c_int, [C.c_void_p, C.c_int]),
+    "emap_wait_for_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "emap_stream_wait_for": (C.c_int, [C.c_void_p, C.c_void_p]),
     "emap_shard_begin": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int64,
                                    C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float]),
     "emap_shard_scratch_bytes": (C.c_int64, [C.c_void_p]),

@@ -35,6 +35,7 @@ struct emap_handle {
   std::string err;
   cudaStream_t stream = nullptr, copy_stream = nullptr, own_stream = nullptr, side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;     // side-stream fork / join of the deferred fusion pushes
+  cudaEvent_t ev_order = nullptr;                       // emap_wait_for_stream / emap_stream_wait_for
   // state
   float* map = nullptr;       // (7,W,W)
   float* map_alt = nullptr;   // shift target
@@ -632,6 +633,7 @@ int emap_create(const emap_config* cfg, int device, emap_handle** out) {
   if ((e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
   if ((e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+  if ((e = cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
   for (int k = 0; k < 9; k++) if ((e = cudaEventCreate(&h->st.ev[k])) != cudaSuccess) return bail("event", e);
 #define ALLOC(p, bytes) if ((e = cudaMalloc(&(p), (bytes))) != cudaSuccess) return bail("cudaMalloc", e)
 #define TRY(call) if ((e = (call)) != cudaSuccess) return bail(#call, e)
@@ -744,6 +746,7 @@ int emap_destroy(emap_handle* h) {
   if (h->copy_done) cudaEventDestroy(h->copy_done);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_order) cudaEventDestroy(h->ev_order);
   if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }
   for (int k = 0; k < 9; k++) if (h->st.ev[k]) cudaEventDestroy(h->st.ev[k]);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1487,6 +1490,20 @@ int emap_set_stream(emap_handle* h, void* s) {
   ENTER(h);
   CK(cudaStreamSynchronize(h->stream));
   h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return EMAP_OK;
+}
+int emap_wait_for_stream(emap_handle* h, void* s) {
+  ENTER(h);
+  if ((cudaStream_t)s == h->stream) return EMAP_OK;
+  CK(cudaEventRecord(h->ev_order, (cudaStream_t)s));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_order, 0));
+  return EMAP_OK;
+}
+int emap_stream_wait_for(emap_handle* h, void* s) {
+  ENTER(h);
+  if ((cudaStream_t)s == h->stream) return EMAP_OK;
+  CK(cudaEventRecord(h->ev_order, h->stream));
+  CK(cudaStreamWaitEvent((cudaStream_t)s, h->ev_order, 0));
   return EMAP_OK;
 }
 int emap_cell_n(const emap_handle* h) { return h ? h->dc.W : EMAP_ERR_INVALID; }

@@ -123,6 +123,19 @@ class ElevationMap:
         no host synchronisation, so it can be captured into a CUDA graph on that stream."""
         self._check(self._L.emap_set_stream(self._h, C.c_void_p(int(cuda_stream_handle or 0))))
 
+    def _after_framework(self):
+        """The handle's next work runs after everything the caller's framework (torch / CuPy current stream) has queued:
+        buffers it wrote are complete, kernels of its that still read the aliased layers are done.  No host sync."""
+        st = _framework_stream()
+        if st is not None:
+            self._check(self._L.emap_wait_for_stream(self._h, C.c_void_p(st)))
+
+    def _before_framework(self):
+        """Work the caller's framework queues from now on runs after everything this handle has queued.  No host sync."""
+        st = _framework_stream()
+        if st is not None:
+            self._check(self._L.emap_stream_wait_for(self._h, C.c_void_p(st)))
+
     def _ptr(self, name):
         p = C.c_void_p()
         self._check(self._L.emap_layer_device_ptr(self._h, name.encode(), C.byref(p)))
@@ -130,7 +143,7 @@ class ElevationMap:
 
     def _tensor(self, name, shape):
         import torch
-        self.synchronize()
+        self._before_framework()      # torch work on the view is ordered after the library's (no host sync)
         return torch.as_tensor(_DevView(self._ptr(name), shape, self), device=f"cuda:{self.device}")
 
     @property
@@ -163,6 +176,7 @@ class ElevationMap:
     # ---- mutators (EM.py:119-226, 420-466, 564-577) ------------------------------------------
     def clear(self):
         with self.map_lock:
+            self._after_framework()
             self._check(self._L.emap_clear(self._h))
             self.semantic_map.clear()                              # EM.py:126
 
@@ -174,10 +188,11 @@ class ElevationMap:
     def move(self, delta_position):
         d = np.ascontiguousarray(np.asarray(delta_position, dtype=np.float64).reshape(3))
         with self.map_lock:
+            self._after_framework()
             self._check(self._L.emap_move(self._h, d.ctypes.data))
             if self.semantic_map.layer_names:                     # EM.py:221 semantic layers move with the map
                 px = np.rint(d[:2] / self.resolution).astype(int)
-                self.synchronize()
+                self._before_framework()
                 self.semantic_map.shift_map_xy((int(px[0]), int(px[1])))
 
     def move_to(self, position, R):
@@ -189,15 +204,18 @@ class ElevationMap:
             if self.semantic_map.layer_names:                     # same cell shift as emap_move_to computes (EM.py:164-170)
                 px = np.rint((p[:2] - self.center[:2].astype(np.float64)) / self.resolution).astype(int)
                 shift = (-int(px[0]), -int(px[1]))
+            self._after_framework()
             self._check(self._L.emap_move_to(self._h, p.ctypes.data, Rm.ctypes.data))
             if shift is not None:
-                self.synchronize()
+                self._before_framework()
                 self.semantic_map.shift_map_xy(shift)
 
     def update_variance(self):
+        self._after_framework()
         self._check(self._L.emap_update_variance(self._h))
 
     def update_time(self):
+        self._after_framework()
         self._check(self._L.emap_update_time(self._h))
 
     def update_normal(self, dilated_map):
@@ -208,7 +226,7 @@ class ElevationMap:
             if cai is None or cai["typestr"] != "<f4" or tuple(cai["shape"]) != (self.cell_n, self.cell_n):
                 raise TypeError("update_normal expects a (cell_n, cell_n) float32 device array")
             ptr = cai["data"][0]
-            _torch_sync()
+            self._after_framework()
         with self.map_lock:
             self._check(self._L.emap_update_normal(self._h, ptr))
 
@@ -224,7 +242,7 @@ class ElevationMap:
         with self.map_lock:
             if dev is not None:
                 ptr, n, row, dt, _keep = dev
-                _torch_sync()
+                self._after_framework()
                 rc = self._L.emap_input_pointcloud(self._h, ptr, n, row, dt, 1, Rm.ctypes.data, tv.ctypes.data,
                                                    float(position_noise), float(orientation_noise))
             else:
@@ -236,6 +254,7 @@ class ElevationMap:
                 if not pts.flags.c_contiguous:
                     pts = np.ascontiguousarray(pts)
                 dt = _lib.EMAP_F32 if pts.dtype == np.float32 else _lib.EMAP_F64
+                self._after_framework()       # framework kernels still reading the aliased layers finish first
                 rc = self._L.emap_input_pointcloud(self._h, pts.ctypes.data, pts.shape[0], pts.shape[1], dt, 0,
                                                    Rm.ctypes.data, tv.ctypes.data, float(position_noise),
                                                    float(orientation_noise))
@@ -266,7 +285,7 @@ class ElevationMap:
         Rm = np.ascontiguousarray(np.stack([np.asarray(_to_host(r), np.float32).reshape(9) for r in Rs]))
         tm = np.ascontiguousarray(np.stack([np.asarray(_to_host(t), np.float32).reshape(3) for t in ts]))
         if device_ptrs:
-            _torch_sync()
+            self._after_framework()
         with self.map_lock:
             self._check(self._L.emap_input_sensors(self._h, ns, ptrs, counts, stride, dt, int(bool(device_ptrs)),
                                                    Rm.ctypes.data, tm.ctypes.data, float(position_noise),
@@ -296,7 +315,7 @@ class ElevationMap:
         if name in self.layer_names:
             return self.elevation_map[self.layer_names.index(name)]
         if name in self.semantic_map.layer_names:
-            self.synchronize()
+            self._before_framework()
             return self.semantic_map.semantic_map[self.semantic_map.layer_names.index(name)]
         if name in self.plugin_manager.layer_names:
             self._update_plugin(name)
@@ -320,13 +339,13 @@ class ElevationMap:
             elif name in self.semantic_map.layer_names:
                 # EM.py:747-748: semantic layers are exported as they are (cropped, flipped), no NaN fill, no z offset
                 m = self.semantic_map.semantic_map[self.semantic_map.layer_names.index(name)]
-                _torch_sync()
+                self._after_framework()
                 self._check(self._L.emap_export_plane(self._h, m.data_ptr(), 0, 0, buf.ctypes.data, n_out))
             elif name in self.plugin_manager.layer_names:
                 self._update_plugin(name)
                 m = self.plugin_manager.get_map_with_name(name)
                 p = self.plugin_manager.get_param_with_name(name)
-                _torch_sync()
+                self._after_framework()
                 self._check(self._L.emap_export_plane(self._h, m.data_ptr(), int(p.fill_nan), int(p.is_height_layer),
                                                       buf.ctypes.data, n_out))
             else:
@@ -358,7 +377,7 @@ class ElevationMap:
                 else:
                     raise KeyError("Layer {} is not in the map".format(name))
             if keep:
-                _torch_sync()
+                self._after_framework()
             self._check(self._L.emap_get_layers(self._h, n, c_names, planes, flags, buf.ctypes.data, n * n_out))
         if not direct:
             data[...] = buf.reshape(data.shape)
@@ -374,6 +393,7 @@ class ElevationMap:
         m = np.ascontiguousarray(elevation_map, np.float32)
         nm = None if normal_map is None else np.ascontiguousarray(normal_map, np.float32)
         c = None if center is None else np.ascontiguousarray(center, np.float64)
+        self._after_framework()
         self._check(self._L.emap_set_state(self._h, m.ctypes.data, None if nm is None else nm.ctypes.data,
                                            None if c is None else c.ctypes.data))
 
@@ -435,11 +455,19 @@ def _to_host(x):
     return np.asarray(x)
 
 
-def _torch_sync():
-    """Order work queued by the caller's framework before the library reads its buffers."""
+def _framework_stream():
+    """CUDA stream handle (int; 0 = legacy default stream) the caller's array framework is queueing work on, or None when
+    no framework is active (or a CUDA-graph capture is running: the caller then runs the handle on the capturing stream)."""
     import sys
     torch = sys.modules.get("torch")
     if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
         if torch.cuda.is_current_stream_capturing():
-            return          # CUDA-graph capture: the caller runs the handle on the capturing stream (emap_set_stream)
-        torch.cuda.current_stream().synchronize()
+            return None
+        return int(torch.cuda.current_stream().cuda_stream)
+    cupy = sys.modules.get("cupy")
+    if cupy is not None:
+        try:
+            return int(cupy.cuda.get_current_stream().ptr)
+        except Exception:
+            return None
+    return None

@@ -1,4 +1,5 @@
-"""Helpers shared by the built-in plugins: call a libemap.so stencil on torch CUDA tensors."""
+"""Helpers shared by the built-in plugins: call a libemap.so stencil on torch CUDA tensors.
+Ordering with the caller's torch stream is by stream waits (ElevationMap._after_framework / _before_framework), never a host sync."""
 import ctypes as C
 
 
@@ -15,8 +16,3 @@ def as_plane(t):
     if not t.is_cuda:
         raise TypeError("plugin layers must be CUDA tensors")
     return t.to(torch.float32).contiguous()
-
-
-def sync_in():
-    import torch
-    torch.cuda.current_stream().synchronize()

@@ -4,7 +4,7 @@ to the host and calls cv2.erode).  Here the same arithmetic runs on the device (
 from typing import List
 
 from .plugin_manager import PluginBase
-from ._engine import require_engine, as_plane, sync_in
+from ._engine import require_engine, as_plane
 
 
 class Erosion(PluginBase):
@@ -32,8 +32,8 @@ class Erosion(PluginBase):
             print(f"No layers are found, using {self.default_layer_name}!")
         layer = as_plane(layer)
         out = torch.empty_like(layer)
-        sync_in()
+        eng._after_framework()
         eng._check(eng._L.emap_erode(eng._h, layer.data_ptr(), out.data_ptr(), self.kernel_size, self.iterations,
                                      int(self.reverse)))
-        eng.synchronize()
+        eng._before_framework()
         return out

@@ -9,7 +9,7 @@ call on large maps and without the two PCIe copies.  `method="ns"` (Navier-Stoke
 from typing import List
 
 from .plugin_manager import PluginBase
-from ._engine import require_engine, as_plane, sync_in
+from ._engine import require_engine, as_plane
 
 
 class Inpainting(PluginBase):
@@ -26,7 +26,7 @@ class Inpainting(PluginBase):
             raise NotImplementedError("Inpainting(method='ns'): the Navier-Stokes variant is not implemented on the device")
         h = as_plane(elevation_map[0]); m = as_plane(elevation_map[2])
         out = torch.empty_like(h)
-        sync_in()
+        eng._after_framework()
         eng._check(eng._L.emap_inpaint(eng._h, h.data_ptr(), m.data_ptr(), out.data_ptr(), self.method))
-        eng.synchronize()
+        eng._before_framework()
         return out

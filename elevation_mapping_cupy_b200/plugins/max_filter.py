@@ -4,7 +4,7 @@ Runs in libemap.so (`emap_max_filter`)."""
 from typing import List
 
 from .plugin_manager import PluginBase
-from ._engine import require_engine, as_plane, sync_in
+from ._engine import require_engine, as_plane
 
 
 class MaxFilter(PluginBase):
@@ -20,8 +20,8 @@ class MaxFilter(PluginBase):
         eng = require_engine(self.engine, "MaxFilter")
         h = as_plane(elevation_map[0]); m = as_plane(elevation_map[2])
         out = torch.empty_like(h)
-        sync_in()
+        eng._after_framework()
         eng._check(eng._L.emap_max_filter(eng._h, h.data_ptr(), m.data_ptr(), out.data_ptr(), self.dilation_size,
                                           self.iteration_n, None))
-        eng.synchronize()
+        eng._before_framework()
         return out

@@ -5,7 +5,7 @@ import ctypes as C
 from typing import List
 
 from .plugin_manager import PluginBase
-from ._engine import require_engine, as_plane, sync_in
+from ._engine import require_engine, as_plane
 
 
 class MinFilter(PluginBase):
@@ -21,8 +21,8 @@ class MinFilter(PluginBase):
         eng = require_engine(self.engine, "MinFilter")
         h = as_plane(elevation_map[0]); m = as_plane(elevation_map[2])
         out = torch.empty_like(h)
-        sync_in()
+        eng._after_framework()
         eng._check(eng._L.emap_min_filter(eng._h, h.data_ptr(), m.data_ptr(), out.data_ptr(), self.dilation_size,
                                           self.iteration_n, None))
-        eng.synchronize()
+        eng._before_framework()
         return out

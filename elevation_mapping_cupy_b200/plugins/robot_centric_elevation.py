@@ -6,7 +6,7 @@ from typing import List
 import numpy as np
 
 from .plugin_manager import PluginBase
-from ._engine import require_engine, as_plane, sync_in
+from ._engine import require_engine, as_plane
 
 
 class RobotCentricElevation(PluginBase):
@@ -27,8 +27,8 @@ class RobotCentricElevation(PluginBase):
         R = rotation.detach().cpu().numpy() if hasattr(rotation, "detach") else np.asarray(rotation)
         R = np.ascontiguousarray(R, dtype=np.float32).reshape(9)
         out = torch.empty_like(h)
-        sync_in()
+        eng._after_framework()
         eng._check(eng._L.emap_robot_centric_elevation(eng._h, h.data_ptr(), m.data_ptr(), R.ctypes.data, out.data_ptr(),
                                                        self.resolution, self.threshold, self.use_threshold))
-        eng.synchronize()
+        eng._before_framework()
         return out

@@ -8,7 +8,7 @@ layer, with the reference's message, when `input_layer_name` is unknown.
 from typing import List
 
 from .plugin_manager import PluginBase
-from ._engine import require_engine, as_plane, sync_in
+from ._engine import require_engine, as_plane
 
 
 class SmoothFilter(PluginBase):
@@ -30,7 +30,7 @@ class SmoothFilter(PluginBase):
         eng = require_engine(self.engine, "SmoothFilter")
         src = as_plane(self._source(elevation_map, layer_names, plugin_layers, plugin_layer_names))
         dst = torch.empty_like(src)
-        sync_in()
+        eng._after_framework()
         eng._check(eng._L.emap_smooth_filter(eng._h, src.data_ptr(), dst.data_ptr()))
-        eng.synchronize()
+        eng._before_framework()
         return dst

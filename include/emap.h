@@ -242,6 +242,14 @@ int emap_stream(emap_handle* h, void** cuda_stream);
 /* Run this handle's work on a caller-owned stream (e.g. the framework's current stream); NULL restores
  * the handle's own stream. */
 int emap_set_stream(emap_handle* h, void* cuda_stream);
+/* Stream ordering WITHOUT host synchronisation between the handle's stream and a stream of the caller's framework
+ * (torch / CuPy current stream; NULL = the legacy default stream): after emap_wait_for_stream the handle's next work runs
+ * after everything queued on `cuda_stream` so far (the caller wrote a buffer the library will read); after
+ * emap_stream_wait_for, work queued on `cuda_stream` from now on runs after everything the handle has queued so far
+ * (the caller will read a layer the library wrote).  The reference has one implicit stream (CuPy's current stream);
+ * these two calls are what keeps that ordering when the library runs on its own stream. */
+int emap_wait_for_stream(emap_handle* h, void* cuda_stream);
+int emap_stream_wait_for(emap_handle* h, void* cuda_stream);
 int emap_cell_n(const emap_handle* h);
 /* Number of kernels this library has launched on the handle since creation (bench.py gpu_launches). */
 int64_t emap_launch_count(const emap_handle* h);

@@ -17,13 +17,18 @@ em = ElevationMap(p)
 pts, R, t = wl.uniform_cloud(0, 1, n=4000, half_extent=2.2)
 cloud = np.concatenate([pts, np.random.default_rng(0).random((len(pts), 2), dtype=np.float32)], 1)
 em.input_pointcloud(cloud, ["x", "y", "z", "a", "rgb"], R, t, 0.02, 0.02)
-out = np.zeros((6, 128, 128), np.float32)
-em.get_maps_with_names_ref(["elevation", "traversability", "min_filter", "smooth", "inpaint", "erosion"], out)
+import os
+layers = ["elevation", "traversability", "min_filter", "smooth", "inpaint", "erosion"]
+if os.environ.get("SKIP_INPAINT"):       # initcheck slows the cooperative march down by > 1000x: covered by memcheck / racecheck only
+    layers.remove("inpaint")
+out = np.zeros((len(layers), 128, 128), np.float32)
+em.get_maps_with_names_ref(layers, out)
 em.move(np.array([0.1, 0.0, 0.0])); em.update_variance(); em.update_time()
 print("sanitizer workload ok")
 PY
 for tool in memcheck racecheck initcheck; do
-  timeout 1200 compute-sanitizer --tool $tool --log-file gpurun_out/sanitizer_${tool}_$tag.log python /tmp/smoke_small.py > gpurun_out/sanitizer_${tool}_$tag.out 2>&1
+  skip=""; [ "$tool" = "initcheck" ] && skip=1
+  SKIP_INPAINT=$skip timeout 240 compute-sanitizer --tool $tool --log-file gpurun_out/sanitizer_${tool}_$tag.log python /tmp/smoke_small.py > gpurun_out/sanitizer_${tool}_$tag.out 2>&1
   echo "$tool exit $?"; tail -3 gpurun_out/sanitizer_${tool}_$tag.log
 done
 # atomic / reduction counters of the frame kernels (north_star: "atomic contention counters")
