@@ -1410,8 +1410,8 @@ int emap_inpaint(emap_handle* h, const float* elevation, const float* is_valid, 
   const int W = h->dc.W, rows = W + 2, cols = W + 2;
   const size_t N = (size_t)rows * cols, C = (size_t)W * W;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  // f, ck, vc0, vc1 (u8 N) | img (u8 C) | T, Tc0, Tc1 (f32 N) | ord (u32 N) | heapA, heapB, children (int N) | ctl
-  const size_t need = 4 * al(N) + al(C) + 3 * al(4 * N) + al(4 * N) + 3 * al(4 * N) + al(sizeof(InpaintCtl));
+  // f, ck, vc0, vc1 (u8 N) | img (u8 C) | T, Tc0, Tc1 (f32 N) | ord (u32 N) | heapA, heapB, children (int N) | ctl | em (u32 N)
+  const size_t need = 4 * al(N) + al(C) + 3 * al(4 * N) + al(4 * N) + 3 * al(4 * N) + al(sizeof(InpaintCtl)) + al(4 * N);
   if (h->ip_bytes < need) {
     CK(cudaStreamSynchronize(h->stream));
     if (h->ip_block) cudaFree(h->ip_block);
@@ -1441,7 +1441,8 @@ int emap_inpaint(emap_handle* h, const float* elevation, const float* is_valid, 
   int* heapA = (int*)b; b += al(4 * N);
   int* heapB = (int*)b; b += al(4 * N);
   int* children = (int*)b; b += al(4 * N);
-  InpaintCtl* ctl = (InpaintCtl*)b;
+  InpaintCtl* ctl = (InpaintCtl*)b; b += al(sizeof(InpaintCtl));
+  v.em = (uint32_t*)b;
   InpaintCtl init;
   memset(&init, 0, sizeof(init));
   init.mm[0] = 0xffffffffu; init.mm[1] = 0u;

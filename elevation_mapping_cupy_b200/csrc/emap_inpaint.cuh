@@ -44,6 +44,8 @@ struct InpaintView {
   uint8_t* ck;                    // popper direction k of the child (0: popper is below, 1: right, 2: above, 3: left)
   float* Tc[2];                   // double-buffered T iterate
   uint8_t* vc[2];                 // double-buffered value iterate
+  uint32_t* em;                   // [rows*cols] per interior child: which of its 12 stencil pixels are known at its event
+                                  // (bits 0..12) / are same-round children filled EARLIER (bits 16..28); see ip_child_masks
 };
 
 // no FMA contraction anywhere: the reference build is plain SSE2
@@ -78,11 +80,12 @@ IP_HD int ip_popper(int cols, int p, int k) {
 
 // strict order of two QUEUE pixels (f == BAND, before or while they are popped): (T, push order)
 IP_HD bool ip_key_less(const InpaintView& v, int a, int b) {
+  // T and push order of a level are fetched together: one memory round trip per level of the popper chains
   const float ta = v.T[a], tb = v.T[b];
+  uint32_t oa = v.ord[a], ob = v.ord[b];
   if (ta != tb) return ta < tb;
   for (int depth = 0; depth < IP_CMP_DEPTH; depth++) {
     if (a == b) return false;
-    const uint32_t oa = v.ord[a], ob = v.ord[b];
     const uint32_t ra = oa >> 3, rb = ob >> 3;
     if (ra != rb) return ra < rb;                                 // pushed in an earlier round
     const int ka = (int)(oa & 7u), kb = (int)(ob & 7u);
@@ -90,8 +93,9 @@ IP_HD bool ip_key_less(const InpaintView& v, int a, int b) {
     const int qa = ip_popper(v.cols, a, ka), qb = ip_popper(v.cols, b, kb);
     if (qa == qb) return ka < kb;
     const float tqa = v.T[qa], tqb = v.T[qb];
+    const uint32_t oqa = v.ord[qa], oqb = v.ord[qb];
     if (tqa != tqb) return tqa < tqb;
-    a = qa; b = qb;                                               // same T: their own push order decides
+    a = qa; b = qb; oa = oqa; ob = oqb;                           // same T: their own push order decides
   }
   return a < b;
 }
@@ -232,19 +236,17 @@ IP_HD bool ip_interior(const InpaintView& v, int c) {
   return i >= 3 && j >= 3 && i <= v.rows - 4 && j <= v.cols - 4;
 }
 
-IP_HD bool ip_eval_child_fast(const InpaintView& v, int c, int cur, float* t_out, uint8_t* val_out) {
-  const int cols = v.cols, W = cols - 2;
+// Which pixels of c's stencil are known at c's event, and which of those are children of the same round filled earlier.
+// The event order of a round is fixed once its children and their first poppers are chosen (pass A): it depends on the
+// queue pixels only, not on the fixed-point iterate.  So the (possibly deep: popper-chain walks on T ties, which regular
+// fronts produce all the time) comparisons are made ONCE per child and round, in the first fixed-point iteration, and
+// cached in v.em; the later iterations read two bit masks.
+IP_HD uint32_t ip_child_masks(const InpaintView& v, int c) {
+  const int cols = v.cols;
   const int off[13] = {0, -cols, -1, 1, cols, -2 * cols, -cols - 1, -cols + 1, -2, 2, cols - 1, cols + 1, 2 * cols};
-  uint8_t F[13], K[13], VC[13], IM[13];
-  float TT[13], TC[13];
-  const int ci = c / cols, cj = c - ci * cols;
-  const int cimg = (ci - 1) * W + (cj - 1);
-  const int offi[13] = {0, -W, -1, 1, W, -2 * W, -W - 1, -W + 1, -2, 2, W - 1, W + 1, 2 * W};
+  uint8_t F[13], K[13];
 #pragma unroll
-  for (int n = 0; n < 13; n++) {                                   // wave 1: independent loads
-    const int x = c + off[n];
-    F[n] = v.f[x]; K[n] = v.ck[x]; TT[n] = v.T[x]; TC[n] = v.Tc[cur][x]; VC[n] = v.vc[cur][x]; IM[n] = v.img[cimg + offi[n]];
-  }
+  for (int n = 0; n < 13; n++) { const int x = c + off[n]; F[n] = v.f[x]; K[n] = v.ck[x]; }       // wave 1
   int Q[13]; float TQ[13]; uint32_t OQ[13];
 #pragma unroll
   for (int n = 0; n < 13; n++) {                                   // wave 2: poppers of the children among them
@@ -252,8 +254,7 @@ IP_HD bool ip_eval_child_fast(const InpaintView& v, int c, int cur, float* t_out
     Q[n] = ch ? ip_popper(cols, c + off[n], K[n]) : c;
     TQ[n] = v.T[Q[n]]; OQ[n] = v.ord[Q[n]];
   }
-  bool kn[13]; float Tn[13]; int val[13];
-  kn[0] = false; Tn[0] = IP_TBIG; val[0] = IM[0];
+  uint32_t m = 0, tie = 0;
 #pragma unroll
   for (int n = 1; n < 13; n++) {
     bool known = false, earlier = false;
@@ -263,10 +264,83 @@ IP_HD bool ip_eval_child_fast(const InpaintView& v, int c, int cur, float* t_out
       if (Q[n] == Q[0]) earlier = K[n] < K[0];
       else if (TQ[n] != TQ[0]) earlier = TQ[n] < TQ[0];
       else if ((OQ[n] >> 3) != (OQ[0] >> 3)) earlier = (OQ[n] >> 3) < (OQ[0] >> 3);
-      else earlier = ip_key_less(v, Q[n], Q[0]);                   // rare: equal T and round, walk the popper chains
+      else tie |= 1u << n;                                         // equal T and round: the popper chains decide (below)
     }
-    kn[n] = known || earlier;
-    Tn[n] = known ? TT[n] : (earlier ? TC[n] : IP_TBIG);
+    if (known || earlier) m |= 1u << n;
+    if (earlier) m |= 1u << (16 + n);
+  }
+  if (tie) {
+    // ip_key_less(Q[n], Q[0]) for every tied n AT ONCE: all comparisons share the chain of c's own popper, and the loads of
+    // one level (T and push order of every chain's next popper) are independent -- one memory round trip per level for the
+    // whole stencil instead of two per level and neighbour.  Operation for operation the loop of ip_key_less.
+    int a[13]; uint32_t oa[13];
+#pragma unroll
+    for (int n = 1; n < 13; n++) { a[n] = Q[n]; oa[n] = OQ[n]; }
+    int b = Q[0]; uint32_t ob = OQ[0];
+    for (int depth = 0; depth < IP_CMP_DEPTH && tie; depth++) {
+      const uint32_t rb = ob >> 3;
+      const int kb = (int)(ob & 7u);
+      const int qb = kb == IP_ROOT ? b : ip_popper(cols, b, kb);
+      int qa[13];
+#pragma unroll
+      for (int n = 1; n < 13; n++) {
+        qa[n] = b;
+        if (!((tie >> n) & 1u)) continue;
+        bool done = true, earlier = false;
+        const uint32_t ra = oa[n] >> 3;
+        const int ka = (int)(oa[n] & 7u);
+        if (a[n] == b) earlier = false;
+        else if (ra != rb) earlier = ra < rb;
+        else if (ka == IP_ROOT || kb == IP_ROOT) earlier = a[n] < b;
+        else {
+          qa[n] = ip_popper(cols, a[n], ka);
+          if (qa[n] == qb) earlier = ka < kb; else done = false;
+        }
+        if (done) { tie &= ~(1u << n); if (earlier) m |= (1u << n) | (1u << (16 + n)); }
+      }
+      if (!tie) break;
+      const float tqb = v.T[qb]; const uint32_t oqb = v.ord[qb];
+      float tqa[13]; uint32_t oqa[13];
+#pragma unroll
+      for (int n = 1; n < 13; n++) { tqa[n] = v.T[qa[n]]; oqa[n] = v.ord[qa[n]]; }            // one wave
+#pragma unroll
+      for (int n = 1; n < 13; n++) {
+        if (!((tie >> n) & 1u)) continue;
+        if (tqa[n] != tqb) { tie &= ~(1u << n); if (tqa[n] < tqb) m |= (1u << n) | (1u << (16 + n)); }
+        else { a[n] = qa[n]; oa[n] = oqa[n]; }
+      }
+      b = qb; ob = oqb;
+    }
+#pragma unroll
+    for (int n = 1; n < 13; n++)                                   // depth cap: the pixel index decides, as in ip_key_less
+      if (((tie >> n) & 1u) && a[n] < b) m |= (1u << n) | (1u << (16 + n));
+  }
+  return m;
+}
+
+// `first`: this is the first fixed-point iteration of the round (compute and cache the masks of c).
+IP_HD bool ip_eval_child_fast(const InpaintView& v, int c, int cur, bool first, float* t_out, uint8_t* val_out) {
+  const int cols = v.cols, W = cols - 2;
+  const int off[13] = {0, -cols, -1, 1, cols, -2 * cols, -cols - 1, -cols + 1, -2, 2, cols - 1, cols + 1, 2 * cols};
+  uint8_t VC[13], IM[13];
+  float TT[13], TC[13];
+  const int ci = c / cols, cj = c - ci * cols;
+  const int cimg = (ci - 1) * W + (cj - 1);
+  const int offi[13] = {0, -W, -1, 1, W, -2 * W, -W - 1, -W + 1, -2, 2, W - 1, W + 1, 2 * W};
+#pragma unroll
+  for (int n = 0; n < 13; n++) {                                   // one wave of independent loads
+    const int x = c + off[n];
+    TT[n] = v.T[x]; TC[n] = v.Tc[cur][x]; VC[n] = v.vc[cur][x]; IM[n] = v.img[cimg + offi[n]];
+  }
+  uint32_t m;
+  if (first) { m = ip_child_masks(v, c); v.em[c] = m; } else m = v.em[c];
+  bool kn[13]; float Tn[13]; int val[13];
+  kn[0] = false; Tn[0] = IP_TBIG; val[0] = IM[0];
+#pragma unroll
+  for (int n = 1; n < 13; n++) {
+    const bool earlier = (m >> (16 + n)) & 1u;
+    kn[n] = (m >> n) & 1u;
+    Tn[n] = (kn[n] && !earlier) ? TT[n] : (earlier ? TC[n] : IP_TBIG);
     val[n] = earlier ? (int)VC[n] : (int)IM[n];
   }
   IpNb up, lf, rt, dn;
@@ -404,7 +478,7 @@ __device__ __forceinline__ bool ip_claim(uint8_t* f, int c) {
 }
 
 // The whole fast-marching replay: one cooperative launch, grid barriers between the passes of a round.
-#define IP_MARCH_THREADS 512
+#define IP_MARCH_THREADS 256
 __global__ void __launch_bounds__(IP_MARCH_THREADS, 1)
 k_ip_march(InpaintView v, int* __restrict__ heapA, int* __restrict__ heapB, int* __restrict__ children, InpaintCtl* ctl,
            int jacobi_cap) {
@@ -446,7 +520,7 @@ k_ip_march(InpaintView v, int* __restrict__ heapA, int* __restrict__ heapB, int*
       for (int e = gtid; e < nchild; e += gsz) {
         const int c = children[e];
         float t; uint8_t val;
-        changed |= ip_interior(v, c) ? ip_eval_child_fast(v, c, cur, &t, &val) : ip_eval_child(v, c, cur, &t, &val);
+        changed |= ip_interior(v, c) ? ip_eval_child_fast(v, c, cur, it == 0, &t, &val) : ip_eval_child(v, c, cur, &t, &val);
         v.Tc[cur ^ 1][c] = t; v.vc[cur ^ 1][c] = val;
       }
       if (changed) atomicOr(&ctl->chg[it % 3], 1);

@@ -15,8 +15,8 @@ extern "C" int inpaint_host(const uint8_t* img_in, const uint8_t* mask, int H, i
   const int rows = H + 2, cols = W + 2, N = rows * cols;
   std::vector<uint8_t> f(N, IP_KNOWN), ck(N, 0), vc0(N, 0), vc1(N, 0), img(img_in, img_in + (size_t)H * W);
   std::vector<float> T(N, IP_TBIG), Tc0(N, 0.f), Tc1(N, 0.f);
-  std::vector<uint32_t> ord(N, IP_ROOT);
-  InpaintView v{rows, cols, f.data(), T.data(), ord.data(), img.data(), ck.data(), {Tc0.data(), Tc1.data()}, {vc0.data(), vc1.data()}};
+  std::vector<uint32_t> ord(N, IP_ROOT), em(N, 0u);
+  InpaintView v{rows, cols, f.data(), T.data(), ord.data(), img.data(), ck.data(), {Tc0.data(), Tc1.data()}, {vc0.data(), vc1.data()}, em.data()};
   // init: INSIDE = mask, BAND = known 4-neighbours of the mask (not on the padding ring)
   for (int i = 1; i < rows - 1; i++)
     for (int j = 1; j < cols - 1; j++)
@@ -60,7 +60,7 @@ extern "C" int inpaint_host(const uint8_t* img_in, const uint8_t* mask, int H, i
       bool changed = false;
       for (int c : children) {
         float t; uint8_t val;
-        if (use_fast && ip_interior(v, c)) changed |= ip_eval_child_fast(v, c, cur, &t, &val);
+        if (use_fast && ip_interior(v, c)) changed |= ip_eval_child_fast(v, c, cur, it == 0, &t, &val);
         else changed |= ip_eval_child(v, c, cur, &t, &val);
         v.Tc[cur ^ 1][c] = t; v.vc[cur ^ 1][c] = val;
       }
