@@ -83,3 +83,17 @@ def test_parallel_rounds_equal_cv2_bit_for_bit():
     got, rounds, max_j, nc = _run_host(L, img, mask)
     assert rounds > 200 and nc == 0
     assert np.array_equal(got, cv2.inpaint(img, mask, 1, cv2.INPAINT_TELEA)), (rounds, max_j)
+
+
+def test_parallel_rounds_expanding_front_equal_cv2():
+    """Config-D-like map: a small known blob in an empty image -- the front expands as smooth rings (T ties at every level of
+    the popper chains: the cached event-order masks and the level-synchronous chain walks decide everything)."""
+    L = _host_lib()
+    W = 300
+    img = np.zeros((W, W), np.uint8); mask = np.ones((W, W), np.uint8)
+    yy, xx = np.mgrid[0:W, 0:W]
+    blob = ((yy - 150) ** 2 + (xx - 140) ** 2 < 25 ** 2)
+    img[blob] = (128 + 60 * np.sin(xx[blob] / 7.0) + 40 * np.cos(yy[blob] / 5.0)).astype(np.uint8); mask[blob] = 0
+    got, rounds, max_j, nc = _run_host(L, np.ascontiguousarray(img), np.ascontiguousarray(mask))
+    assert rounds > 150 and nc == 0
+    assert np.array_equal(got, cv2.inpaint(img, mask, 1, cv2.INPAINT_TELEA)), (rounds, max_j)
