@@ -527,8 +527,10 @@ int make_post_tm(emap_handle* h, int which, const float* base) {
   memset(&h->post_tm[which], 0, sizeof(CUtensorMap));
   h->post_tm_base[which] = base;
   const int W = h->dc.W;
-  if (W % 4 != 0) return 0;                                  // k_post stages with plain loads
   const int HL = h->dc.dilation + 3, HLX = (HL + 3) & ~3;
+  // plain loads instead when the row pitch is not a multiple of 16 bytes, or the map is smaller than one staged box
+  h->dc.post_tma = (W % 4 == 0 && W >= PT_X + 2 * HLX && W >= PT_Y + 2 * HL) ? 1 : 0;
+  if (!h->dc.post_tma) return 0;
   const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)W, 7};
   const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * W * 4};
   const cuuint32_t box[3] = {(cuuint32_t)(PT_X + 2 * HLX), (cuuint32_t)(PT_Y + 2 * HL), 1};

@@ -907,7 +907,7 @@ k_post(const DevCfg c, float* __restrict__ map, float* __restrict__ trav_input, 
   // Stage upper_bound / is_valid / is_upper_bound for the tile + halo: three TMA tensor copies (cp.async.bulk.tensor.3d
   // of a B x A x 1 box of the (W, W, 7) state tensor; elements outside the map arrive as zeros) completing on one
   // mbarrier.  Maps whose row pitch is not a multiple of 16 bytes cannot be described to the TMA unit: plain loads.
-  const bool bulk = (W % 4 == 0);
+  const bool bulk = c.post_tma != 0;
   if (bulk) {
     const u32 sbar = (u32)__cvta_generic_to_shared(s_bar);
     if (tid == 0) {
